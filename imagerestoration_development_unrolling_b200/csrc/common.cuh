@@ -1,0 +1,152 @@
+// common.cuh - shared helpers for the GLR/GTV kernels (sm_100a).
+//
+// Every kernel in this directory is written against blockDim-agnostic strided loops
+// (`for (i = threadIdx.x; i < n; i += blockDim.x)`) with __syncthreads() only BETWEEN loops and
+// block reductions only through block_sum().  That style is what lets tests/emu compile the very
+// same sources with g++ (-DGLRGTV_EMU: one "thread" per block, blocks run sequentially) and check
+// the index arithmetic and border rules on a machine without a GPU.  The emulation build is test
+// infrastructure: the product library is always the nvcc build.
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/glrgtv.h"
+
+#ifdef GLRGTV_EMU
+// ------------------------------------------------------------------ CPU emulation shim (tests only)
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+struct emu_dim3 {
+    unsigned x = 1, y = 1, z = 1;
+    emu_dim3() {}
+    emu_dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+typedef emu_dim3 dim3;
+extern thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+extern thread_local float* emu_smem;  // 256 KB scratch playing the role of dynamic shared memory
+static inline void __syncthreads() {}
+static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
+static inline float __ldg(const float* p) { return *p; }
+typedef void* cudaStream_t;
+#define GLR_SMEM_DECL(name) float* name = emu_smem
+#define GLR_LAUNCH(kernel, grid, block, smem_bytes, stream, ...)                       \
+    do {                                                                               \
+        emu_dim3 g_ = (grid);                                                          \
+        gridDim = g_;                                                                  \
+        blockDim = emu_dim3(1, 1, 1);                                                  \
+        threadIdx = emu_dim3(0, 0, 0);                                                 \
+        for (unsigned bz_ = 0; bz_ < g_.z; ++bz_)                                      \
+            for (unsigned by_ = 0; by_ < g_.y; ++by_)                                  \
+                for (unsigned bx_ = 0; bx_ < g_.x; ++bx_) {                            \
+                    blockIdx = emu_dim3(bx_, by_, bz_);                                \
+                    kernel(__VA_ARGS__);                                               \
+                }                                                                      \
+    } while (0)
+#define GLR_CHECK_LAUNCH() GLRGTV_OK
+static inline int glr_memset_async(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
+#else
+// ------------------------------------------------------------------ CUDA build
+#include <cuda_runtime.h>
+#define GLR_SMEM_DECL(name) extern __shared__ __align__(16) float name[]
+#define GLR_LAUNCH(kernel, grid, block, smem_bytes, stream, ...) \
+    kernel<<<(grid), (block), (smem_bytes), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+int glr_record_launch_error(void);
+#define GLR_CHECK_LAUNCH() glr_record_launch_error()
+static inline int glr_memset_async(void* p, int v, size_t n, cudaStream_t s) {
+    return cudaMemsetAsync(p, v, n, s) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+#define GLR_THREADS 256
+
+// ------------------------------------------------------------------ small device helpers
+__host__ __device__ __forceinline__ int glr_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__host__ __device__ __forceinline__ int glr_reflecti(int v, int n) {
+    // torch 'reflect' padding by one pixel: -1 -> 1, n -> n-2
+    if (v < 0) v = -v;
+    if (v > n - 1) v = 2 * (n - 1) - v;
+    return v;
+}
+__host__ __device__ __forceinline__ int glr_mapi(int v, int n, int pad_mode) {
+    return pad_mode == GLRGTV_PAD_CLAMP ? glr_clampi(v, 0, n - 1) : glr_reflecti(v, n);
+}
+__host__ __device__ __forceinline__ bool glr_inside(int h, int w, int H, int W) {
+    return h >= 0 && h < H && w >= 0 && w < W;
+}
+// all p in [0,n) with clamp(p+d,0,n-1) == q, as an inclusive range [lo,hi] (empty when lo>hi)
+__host__ __device__ __forceinline__ void glr_clamp_preimage(int q, int d, int n, int& lo, int& hi) {
+    lo = q - d;
+    hi = q - d;
+    if (q == 0) lo = 0;
+    if (q == n - 1) hi = n - 1;
+    if (lo < 0) lo = 0;
+    if (hi > n - 1) hi = n - 1;
+}
+
+// five taps of the stats kernel, order c, R, D, U, L  (offsets (0,0),(0,1),(1,0),(-1,0),(0,-1))
+struct StatsTaps {
+    float kc, kr, kd, ku, kl;
+};
+__host__ __device__ __forceinline__ StatsTaps glr_taps(float p1, float pa, float pb, float p3) {
+    StatsTaps t;
+    t.kc = ((p1 - pa) - pb) + 4.0f * p3;
+    t.kr = pa - p3;
+    t.kd = pb - p3;
+    t.ku = -p3;
+    t.kl = -p3;
+    return t;
+}
+__device__ __forceinline__ StatsTaps glr_load_taps(const glrgtv_stats& st, int c) {
+    int i = st.n == 1 ? 0 : c;
+    return glr_taps(st.p01[i], st.p02a[i], st.p02b[i], st.p03[i]);
+}
+
+// block-wide sum; result valid in thread 0 (emu: single thread).  `red` = >= 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#ifdef GLRGTV_EMU
+    (void)red;
+    return v;
+#else
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+    if (wid == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return v;
+#endif
+}
+
+static inline int glr_shape_ok(const glrgtv_shape* s) {
+    return s && s->B > 0 && s->G > 0 && s->F > 0 && s->H > 0 && s->W > 0;
+}
+static inline int glr_window_ok(const glrgtv_window* w) {
+    return w && w->n_edges > 0 && w->n_edges <= GLRGTV_MAX_EDGES;
+}
+static inline int glr_aligned(const void* p) { return p && (((uintptr_t)p) & 3u) == 0; }
+#define GLR_REQUIRE_PTR(p)                               \
+    do {                                                 \
+        if (!glr_aligned(p)) return GLRGTV_ERR_POINTER;  \
+    } while (0)
+
+// grid helper: planes in x (limit 2^31-1), pixel chunks in y
+static inline dim3 glr_grid(long planes, long pixels, int per_block) {
+    long chunks = (pixels + per_block - 1) / per_block;
+    if (chunks > 65535) chunks = 65535;
+    return dim3((unsigned)planes, (unsigned)chunks, 1);
+}

@@ -1,0 +1,200 @@
+/*
+ * glrgtv.h - C ABI of libglrgtv.so: hand-written sm_100a CUDA for the unrolled
+ * graph-Laplacian-regulariser (GLR) / graph-total-variation (GTV) restoration blocks.
+ *
+ * The reference (tamthuc1995/ImageRestoration-Development-Unrolling) is pure PyTorch and has no FFI
+ * of its own; every entry point below names the reference method it replaces.  V1X0 =
+ * exploration/GGTV_GGLR_v1.0/deep_multiscale_GGLR_GGTV_v1x0.py (== LIB/model_GLR_GTV_deep_v13.py),
+ * V7 = exploration/model_multiscale_mixture_GLR/lib/model_GLR_GTV_deep_v7.py.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous float32 unless it says "host";
+ *  - signals  are [B, G, F, H, W]   (== the reference's [B, C, H, W] with c = g*F + f);
+ *    weights  are [B, G, E, H, W];  edge signals are [B, G, F, E, H, W];
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it, nothing synchronises,
+ *    nothing allocates; outputs and workspaces belong to the caller;
+ *  - "accumulated" outputs (parameter gradients) are ADDED to: the caller zeroes them;
+ *  - return value: GLRGTV_OK or a negative glrgtv_status.  CUDA launch errors are reported through
+ *    cudaGetLastError() -> GLRGTV_ERR_CUDA (glrgtv_last_cuda_error() gives the text).
+ *  - there is no CPU fallback: host pointers are an error the driver will report at run time.
+ */
+#ifndef GLRGTV_H
+#define GLRGTV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLRGTV_ABI_VERSION 1
+#define GLRGTV_MAX_EDGES 48 /* 7x7 full window */
+
+typedef enum glrgtv_status {
+    GLRGTV_OK = 0,
+    GLRGTV_ERR_SHAPE = -1,     /* non-positive / odd / inconsistent sizes        */
+    GLRGTV_ERR_POINTER = -2,   /* NULL or misaligned pointer                     */
+    GLRGTV_ERR_CUDA = -3,      /* launch failed, see glrgtv_last_cuda_error()    */
+    GLRGTV_ERR_DEVICE = -4,    /* current device is not sm_100                   */
+    GLRGTV_ERR_WORKSPACE = -5, /* workspace smaller than *_workspace_bytes()     */
+    GLRGTV_ERR_UNSUPPORTED = -6
+} glrgtv_status;
+
+typedef enum glrgtv_pad { GLRGTV_PAD_CLAMP = 0, GLRGTV_PAD_REFLECT = 1 } glrgtv_pad;
+
+/* signal geometry */
+typedef struct glrgtv_shape {
+    int32_t B, G, F, H, W;
+} glrgtv_shape;
+
+/* neighbour stencil: edge e connects p -> p + (dh[e], dw[e]); order as V1X0:42-49 / V7:284-298 */
+typedef struct glrgtv_window {
+    int32_t n_edges;
+    int32_t dh[GLRGTV_MAX_EDGES];
+    int32_t dw[GLRGTV_MAX_EDGES];
+} glrgtv_window;
+
+/* the four stats_kernel_p* parameters of one GLRFast/GTVFast (V1X0:66-118).  n = C (V1X0, per channel)
+ * or 1 (V7:311-363, scalars shared by all channels).  pad = CLAMP for V1X0:186, REFLECT for V7:458 */
+typedef struct glrgtv_stats {
+    const float* p01;
+    const float* p02a;
+    const float* p02b;
+    const float* p03;
+    int32_t n;
+    int32_t pad;
+} glrgtv_stats;
+
+int glrgtv_abi_version(void);
+const char* glrgtv_last_cuda_error(void);
+/* 0 when the current CUDA device can run this library (compute capability 10.x) */
+int glrgtv_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-operator entry points (public methods of GLRFast / GTVFast)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* GLRFast/GTVFast.extract_edge_weights (V1X0:160-175, 391-407): feat [B,G,F,H,W], multiM [G,F] -> w [B,G,E,H,W] */
+int glrgtv_edge_weights_fwd(const glrgtv_shape* s, const glrgtv_window* win, const float* feat,
+                            const float* multiM, float* w, void* stream);
+/* VJP: gw [B,G,E,H,W] -> gfeat [B,G,F,H,W] (written), gmultiM [G,F] (accumulated).
+ * scratch: B*G*E*H*W floats (the softmax-VJP of gw). */
+int glrgtv_edge_weights_bwd(const glrgtv_shape* s, const glrgtv_window* win, const float* feat,
+                            const float* multiM, const float* w, const float* gw, float* gfeat,
+                            float* gmultiM, float* scratch, void* stream);
+
+/* normalize_and_transform_features (V1X0:146-157): out = multiM * feat / max(|feat|_F, 1e-12).
+ * bwd: gfeat written, gmultiM accumulated. */
+int glrgtv_normalize_fwd(const glrgtv_shape* s, const float* feat, const float* multiM, float* out, void* stream);
+int glrgtv_normalize_bwd(const glrgtv_shape* s, const float* feat, const float* multiM, const float* g,
+                         float* gfeat, float* gmultiM, void* stream);
+/* get_neighbors_pixels (V1X0:128-144): out [B,G,F,E,H,W] = x[cl(p+d_e)]; bwd scatters back. */
+int glrgtv_gather_neighbors_fwd(const glrgtv_shape* s, const glrgtv_window* win, const float* x, float* out,
+                                void* stream);
+int glrgtv_gather_neighbors_bwd(const glrgtv_shape* s, const glrgtv_window* win, const float* g, float* gx,
+                                void* stream);
+
+/* stats_conv (V1X0:177-195): out = S x.   bwd: gx written; gstats[4*n] accumulated, order p01,p02a,p02b,p03 */
+int glrgtv_stats_conv_fwd(const glrgtv_shape* s, const glrgtv_stats* st, const float* x, float* out, void* stream);
+int glrgtv_stats_conv_bwd(const glrgtv_shape* s, const glrgtv_stats* st, const float* x, const float* g,
+                          float* gx, float* gstats, void* stream);
+/* stats_conv_transpose (V1X0:197-215) */
+int glrgtv_stats_conv_t_fwd(const glrgtv_shape* s, const glrgtv_stats* st, const float* y, float* out, void* stream);
+int glrgtv_stats_conv_t_bwd(const glrgtv_shape* s, const glrgtv_stats* st, const float* y, const float* g,
+                            float* gy, float* gstats, void* stream);
+
+/* GLRFast.op_L_norm (V1X0:218-228): out = x - sum_e w_e x[cl(p+d_e)].  bwd: gx, gw written. */
+int glrgtv_op_L_fwd(const glrgtv_shape* s, const glrgtv_window* win, const float* x, const float* w,
+                    float* out, void* stream);
+int glrgtv_op_L_bwd(const glrgtv_shape* s, const glrgtv_window* win, const float* x, const float* w,
+                    const float* g, float* gx, float* gw, void* stream);
+
+/* GTVFast.op_C after its stats_conv (V1X0:459-467): z[b,g,f,e] = w_e (sx - sx[cl(p+d_e)]) */
+int glrgtv_op_C_fwd(const glrgtv_shape* s, const glrgtv_window* win, const float* sx, const float* w,
+                    float* z, void* stream);
+int glrgtv_op_C_bwd(const glrgtv_shape* s, const glrgtv_window* win, const float* sx, const float* w,
+                    const float* gz, float* gsx, float* gw, void* stream);
+/* GTVFast.op_C_transpose before its stats_conv_transpose (V1X0:471-513) */
+int glrgtv_op_Ct_fwd(const glrgtv_shape* s, const glrgtv_window* win, const float* z, const float* w,
+                     float* o, void* stream);
+int glrgtv_op_Ct_bwd(const glrgtv_shape* s, const glrgtv_window* win, const float* z, const float* w,
+                     const float* go, float* gz, float* gw, void* stream);
+
+/* MixtureGTVGLR.soft_threshold (V1X0:684-704): t [B,G,F,E,H,W], thr [G] (already exp'd) */
+int glrgtv_soft_threshold_fwd(const glrgtv_shape* s, int n_edges, const float* t, const float* thr,
+                              float* out, void* stream);
+/* gt written, gthr [G] accumulated */
+int glrgtv_soft_threshold_bwd(const glrgtv_shape* s, int n_edges, const float* t, const float* thr,
+                              const float* g, float* gt, float* gthr, void* stream);
+
+/* 2x2 mean pooling P (V1X0:613, 662-665) and its transpose (V1X0:676-679); each is the other's VJP.
+ * `s` is always the FINE geometry (H, W even); coarse tensors are [B,G,F,H/2,W/2]. */
+int glrgtv_pool2_fwd(const glrgtv_shape* s, const float* fine, float* coarse, void* stream);
+int glrgtv_unpool2_fwd(const glrgtv_shape* s, const float* coarse, float* fine, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused block: LocalLowpassFilteringBlock / MixtureGTVGLR (V1X0:707-811, 985-988), 3x3 cross window
+ * ---------------------------------------------------------------------------------------------- */
+
+/* parameters of one GLRFast / GTVFast inside the block */
+typedef struct glrgtv_opparams {
+    glrgtv_stats stats; /* n = C, pad = CLAMP */
+    const float* multiM; /* [G,F] */
+} glrgtv_opparams;
+
+/* all parameters of MixtureGTVGLR that the stencil kernels read (the 1x1 / 2x2 projections are plain
+ * GEMMs done by the caller; their outputs arrive as feat0 / feat1) */
+typedef struct glrgtv_block_params {
+    glrgtv_opparams gtv0, glr0, gtv1, glr1; /* GTVmodule00, GLRmodule00, GTVmodule01, GLRmodule01 */
+    const float* alpha;  /* alphaCGD [3,G]          V1X0:546 */
+    const float* beta;   /* betaCGD  [3,G]          V1X0:551 */
+    const float* mu0;    /* muys00  [G] (log)       V1X0:582 */
+    const float* ro0;    /* ro00    [G] (log)       V1X0:568 */
+    const float* gamma0; /* gamma00 [G] (log)       V1X0:572 */
+    const float* mu1;    /* muys01  [G] (log) */
+    const float* ro1;    /* ro01    [G] (log) */
+    const float* gamma1; /* gamma01 [G] (log) */
+    const float* skip;   /* LocalLowpassFilteringBlock.skip_weight [2]; NULL => out = filter(x) */
+} glrgtv_block_params;
+
+/* gradients of the above, same layout, all ACCUMULATED (caller zeroes).  stats pointers are written
+ * as mutable floats; n/pad are ignored. */
+typedef struct glrgtv_block_grads {
+    float *gtv0_stats, *glr0_stats, *gtv1_stats, *glr1_stats; /* each [4*C]: p01,p02a,p02b,p03 */
+    float *gtv0_M, *glr0_M, *gtv1_M, *glr1_M;                 /* each [G,F] */
+    float *alpha, *beta;                                      /* [3,G] */
+    float *mu0, *ro0, *gamma0, *mu1, *ro1, *gamma1;           /* [G]   */
+    float* skip;                                              /* [2] or NULL */
+} glrgtv_block_grads;
+
+/* activations kept between forward and backward (all written by glrgtv_block_fwd, caller-owned):
+ *   w  : 4 weight sets  wT0,wL0 [B,G,4,H,W]  wT1,wL1 [B,G,4,H/2,W/2]
+ *   bA, x1, bB, r1, x2 : [B,G,F,H,W] each                                    */
+typedef struct glrgtv_block_saved {
+    float *wT0, *wL0, *wT1, *wL1;
+    float *bA, *x1, *bB, *r1, *x2;
+} glrgtv_block_saved;
+
+/* x [B,C,H,W]; feat0 = patchs_features_extraction00(x) [B,2C,H,W]; feat1 = ..01(x) [B,2C,H/2,W/2]
+ * (first C channels feed GTV, last C feed GLR, V1X0:714, 726);  out [B,C,H,W]. */
+int glrgtv_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, const float* x,
+                     const float* feat0, const float* feat1, float* out, const glrgtv_block_saved* saved,
+                     void* stream);
+
+size_t glrgtv_block_bwd_workspace_bytes(const glrgtv_shape* s);
+/* gout [B,C,H,W] -> gx [B,C,H,W] (the direct path, WITHOUT the feature-path term),
+ * gfeat0 [B,2C,H,W], gfeat1 [B,2C,H/2,W/2] (for the caller's GEMM backward), and parameter grads. */
+int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params* p, const float* x,
+                     const float* feat0, const float* feat1, const glrgtv_block_saved* saved,
+                     const float* gout, float* gx, float* gfeat0, float* gfeat1,
+                     const glrgtv_block_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Host-buffer convenience for embedding without PyTorch: copies x/feat in, runs glrgtv_block_fwd on
+ * `stream`, copies out back; all device memory comes from `workspace` (device, >= the size below). */
+size_t glrgtv_block_fwd_host_workspace_bytes(const glrgtv_shape* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLRGTV_H */
