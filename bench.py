@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the GLR/GTV hot path (BASELINE.json metric: Mpix/s).
+
+Workload (config[1], "model_multiscale_mixture_GLR denoising training, 256x256 patches, batch 32"):
+one training pass (forward + backward, all parameter gradients) of the FOUR LocalLowpassFilteringBlock
+of the shipped v13 model on the feature maps a 32 x 3 x 256 x 256 batch produces
+    [32,48,256,256] G=8   [32,96,128,128] G=16   [32,192,64,64] G=16   [32,384,32,32] G=32
+A "step" = that pass; pixels = B*256*256 network-input pixels per rank.  Synthetic N(0,1) feature maps,
+default-init (random projection) weights.  The host CNN around the blocks is out of the hot path
+ and is not run.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N>1: launched under torchrun, one rank per GPU; batch-sharded (every rank its own 32-image batch, weak
+scaling) with ONE NCCL all-reduce of the flattened block-parameter gradients per step inside the timed region.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS, NGRAPHS = [48, 96, 192, 384], [8, 16, 16, 32]
+BATCH, RES = 32, 256
+METRIC, UNIT = "train_Mpix_per_s", "Mpix/s"
+WORKLOAD = ("v13 four LocalLowpassFilteringBlock fwd+bwd on feature maps of a 32x3x256x256 batch "
+            "([32,48,256,256],[32,96,128,128],[32,192,64,64],[32,384,32,32])")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="per-rank batch (default = the config's 32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_blocks_state(seed=0):
+    """default-init state dicts of the four blocks, built WITHOUT the product package's kernels
+    (module construction is plain torch)."""
+    import torch
+    from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
+    torch.manual_seed(seed)
+    return [{k: v.detach().clone() for k, v in M.LocalLowpassFilteringBlock(d, 1, g).state_dict().items()}
+            for d, g in zip(DIMS, NGRAPHS)]
+
+
+def cpu_port_step(states, xs, gs):
+    """one fwd+bwd of the four blocks with the oracle port (torch CPU, all threads)."""
+    from oracle import glr_gtv_oracle as O
+    for sd, x, g in zip(states, xs, gs):
+        O.lowpass_block_fwd_bwd(sd, x, g)
+
+
+def cpu_sample(batch, seed=1):
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    xs = [torch.randn(batch, d, RES >> s, RES >> s, generator=gen) for s, d in enumerate(DIMS)]
+    gs = [torch.randn(batch, d, RES >> s, RES >> s, generator=gen) for s, d in enumerate(DIMS)]
+    return xs, gs
+
+
+def run_cpu(steps, warmup, sample_batch=1):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    states = cpu_blocks_state()
+    xs, gs = cpu_sample(sample_batch)
+    for _ in range(warmup):
+        cpu_port_step(states, xs, gs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_port_step(states, xs, gs)
+    dt = (time.perf_counter() - t0) / steps
+    mpix = sample_batch * RES * RES / dt / 1e6
+    return mpix, dt, cores
+
+
+def reference_arm(a):
+    """`--impl reference`: the reference is pure Python/PyTorch and /root/reference does not exist on the GPU box,
+    so the oracle PORT (same ATen arithmetic, oracle/glr_gtv_oracle.py) is timed on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mpix, dt, cores = run_cpu(a.steps, a.warmup)
+    sample = f"batch 1 of the {BATCH} (65,536 px per step), forward+backward of the four blocks, torch CPU {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                if t0 - 0.05 <= t <= t1 + 0.15:
+                    sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if t0 - 0.05 <= t <= t1 + 0.15 and v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ roofline bookkeeping
+SLOTS = ["fwd_weights", "fwd_BA", "fwd_X1", "fwd_X2", "fwd_X3", "bwd_X3", "bwd_X2", "bwd_X1", "bwd_BA", "bwd_weights"]
+
+
+def algorithmic_bytes(slot, B):
+    """fp32 bytes one step moves through kernel `slot`, summed over the four scales: every operand tensor read
+    once + every result written once (DESIGN.md 'algorithmic bytes'); halo re-reads are not algorithmic."""
+    total = 0
+    for s, (C, G) in enumerate(zip(DIMS, NGRAPHS)):
+        N = B * (RES >> s) * (RES >> s)
+        GE = 4 * G
+        per_px = {
+            "fwd_weights": 1.25 * (2 * C + 2 * GE),
+            "fwd_BA": 2 * C + 1.25 * GE,
+            "fwd_X1": 2 * C + 2.5 * GE,
+            "fwd_X2": 5 * C + 2.5 * GE,
+            "fwd_X3": 5 * C + 2.5 * GE,
+            "bwd_X3": 6 * C + 5 * GE,
+            "bwd_X2": 5 * C + 7.5 * GE,
+            "bwd_X1": 3 * C + 7.5 * GE,
+            "bwd_BA": 5 * C + 3.75 * GE,
+            "bwd_weights": 2.5 * (2 * C + 2 * GE),
+        }[slot]
+        total += per_px * N * 4
+    return total
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+    from imagerestoration_development_unrolling_b200 import _lib as L
+    from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False           # fp32 projections: the parity setting is the measured one
+    torch.backends.cuda.matmul.allow_tf32 = False
+    lib = L.load()
+    L.check(lib.glrgtv_check_device(), lib, "check_device")
+
+    B = a.batch
+    torch.manual_seed(0)
+    blocks = [M.LocalLowpassFilteringBlock(d, 1, g).to(dev) for d, g in zip(DIMS, NGRAPHS)]
+    params = [p for b in blocks for p in b.parameters()]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    shapes = [(B, d, RES >> s, RES >> s) for s, d in enumerate(DIMS)]
+    xs = [torch.randn(sh, device=dev, generator=gen).requires_grad_(True) for sh in shapes]
+    gs = [torch.randn(sh, device=dev, generator=gen) for sh in shapes]
+    flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+
+    def step(inputs):
+        outs = [blk(x) for blk, x in zip(blocks, inputs)]
+        torch.autograd.backward(outs, gs, inputs=list(inputs) + params)
+        if world > 1:                                   # data-parallel training: gradient all-reduce over NVLink
+            torch.cat([p.grad.reshape(-1) for p in params], out=flat_grad)
+            dist.all_reduce(flat_grad)
+        for p in params:
+            p.grad = None
+        for x in inputs:
+            x.grad = None
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step(xs)
+    barrier()
+
+    # ---- timed region (device-resident inputs), per-kernel events on, clocks sampled
+    clocks = ClockSampler(local) if rank == 0 else None
+    lib.glrgtv_profile_enable(1)
+    launches0 = lib.glrgtv_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        step(xs)
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    lib.glrgtv_profile_enable(0)
+    launches = lib.glrgtv_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clk = clocks.stop(t0, t1) if clocks else None
+    slot_ms = (ctypes.c_float * 16)()
+    slot_n = (ctypes.c_int * 16)()
+    lib.glrgtv_profile_read(slot_ms, slot_n, 16)
+
+    # ---- end-to-end: pinned host inputs -> device -> fwd+bwd -> loss back on the host, every step
+    hx = [torch.randn(sh).pin_memory() for sh in shapes]
+    dbuf = [torch.empty(sh, device=dev) for sh in shapes]
+
+    def e2e_step():
+        ins = []
+        for h, d in zip(hx, dbuf):
+            d.copy_(h, non_blocking=True)
+            ins.append(d.detach().requires_grad_(True))
+        outs = step(ins)
+        loss = sum(o.mean() for o in outs)
+        return float(loss.item())                        # D2H read of the step's result
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(a.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+
+    if rank == 0:
+        pix = B * RES * RES * world
+        value = pix * a.steps / (ms / 1e3) / 1e6
+        e2e_value = pix * a.steps / (ms_e2e / 1e3) / 1e6
+        # dominant kernel of the step and its roofline
+        per_slot = {SLOTS[i]: (slot_ms[i], slot_n[i]) for i in range(len(SLOTS)) if slot_n[i] > 0}
+        top = max(per_slot, key=lambda k: per_slot[k][0])
+        top_ms_per_step = per_slot[top][0] / a.steps
+        peak, peak_src = measured_peaks()
+        achieved = algorithmic_bytes(top, B) / (top_ms_per_step / 1e3) / 1e9
+        whole_ms = sum(v[0] for v in per_slot.values()) / a.steps
+        roofline = {
+            "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": peak_src, "traffic": None,
+            "kernel_ms_per_step": {k: round(v[0] / a.steps, 4) for k, v in per_slot.items()},
+            "kernel_share_of_step": round(top_ms_per_step / (ms / a.steps), 4),
+            "own_kernels_share_of_step": round(whole_ms / (ms / a.steps), 4),
+            "whole_block_compulsory_GBs": sum(20 * C * B * (RES >> s) ** 2 for s, C in enumerate(DIMS)) / (ms / a.steps / 1e3) / 1e9,
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_rank_batch": B, "parallelism": f"dp{world}",
+                       "l2": "inputs larger than L2 (755 MB of block inputs per step)", "tf32": False},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                    "h2d_bytes_per_step": int(sum(h.numel() for h in hx) * 4), "d2h_bytes_per_step": 4},
+            "roofline": roofline,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            mpix, dt, cores = run_cpu(steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "batch 1 of the 32 (65,536 px), fwd+bwd of the four blocks, 1 warm-up + 2 reps, "
+                                              f"oracle port on torch CPU with {cores} threads"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

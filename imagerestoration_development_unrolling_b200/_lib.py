@@ -69,6 +69,9 @@ _SIGS = {
     "glrgtv_abi_version": (C.c_int, []),
     "glrgtv_last_cuda_error": (C.c_char_p, []),
     "glrgtv_check_device": (C.c_int, []),
+    "glrgtv_launch_count": (C.c_ulonglong, []),
+    "glrgtv_profile_enable": (C.c_int, [C.c_int]),
+    "glrgtv_profile_read": (C.c_int, [_P(C.c_float), _P(C.c_int), C.c_int]),
     "glrgtv_edge_weights_fwd": (C.c_int, [_P(Shape), _P(Window), fp, fp, fp, fp]),
     "glrgtv_edge_weights_bwd": (C.c_int, [_P(Shape), _P(Window), fp, fp, fp, fp, fp, fp, fp, fp]),
     "glrgtv_normalize_fwd": (C.c_int, [_P(Shape), fp, fp, fp, fp]),

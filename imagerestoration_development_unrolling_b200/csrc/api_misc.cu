@@ -9,6 +9,9 @@ extern "C" {
 int glrgtv_abi_version(void) { return GLRGTV_ABI_VERSION; }
 const char* glrgtv_last_cuda_error(void) { return "emulation build"; }
 int glrgtv_check_device(void) { return GLRGTV_OK; }
+unsigned long long glrgtv_launch_count(void) { return 0; }
+int glrgtv_profile_enable(int) { return 0; }
+int glrgtv_profile_read(float*, int*, int) { return 0; }
 }
 #else
 #include <string.h>
@@ -21,7 +24,58 @@ int glr_record_launch_error(void) {
     return GLRGTV_ERR_CUDA;
 }
 
+unsigned long long g_glr_launches = 0;
+int g_glr_prof_on = 0;
+#define GLR_PROF_SLOTS 32
+#define GLR_PROF_POOL 8192
+static cudaEvent_t g_ev[GLR_PROF_POOL][2];
+static int g_ev_slot[GLR_PROF_POOL];
+static int g_ev_made = 0, g_ev_used = 0, g_ev_open[GLR_PROF_SLOTS];
+
+void glr_prof_mark(int slot, int end, void* stream) {
+    if (slot < 0 || slot >= GLR_PROF_SLOTS) return;
+    if (!end) {
+        if (g_ev_used >= GLR_PROF_POOL) { g_ev_open[slot] = -1; return; }
+        if (g_ev_used >= g_ev_made) {
+            if (cudaEventCreate(&g_ev[g_ev_made][0]) != cudaSuccess || cudaEventCreate(&g_ev[g_ev_made][1]) != cudaSuccess) {
+                g_ev_open[slot] = -1;
+                return;
+            }
+            ++g_ev_made;
+        }
+        g_ev_slot[g_ev_used] = slot;
+        g_ev_open[slot] = g_ev_used;
+        cudaEventRecord(g_ev[g_ev_used][0], (cudaStream_t)stream);
+        ++g_ev_used;
+    } else if (g_ev_open[slot] >= 0) {
+        cudaEventRecord(g_ev[g_ev_open[slot]][1], (cudaStream_t)stream);
+        g_ev_open[slot] = -1;
+    }
+}
+
 extern "C" {
+unsigned long long glrgtv_launch_count(void) { return g_glr_launches; }
+// start (on=1: also clears) / stop recording one CUDA-event pair around every kernel of the block entry points
+int glrgtv_profile_enable(int on) {
+    if (on) {
+        g_ev_used = 0;
+        for (int i = 0; i < GLR_PROF_SLOTS; ++i) g_ev_open[i] = -1;
+    }
+    g_glr_prof_on = on;
+    return GLRGTV_OK;
+}
+// synchronises on the recorded events; ms[slot] = summed duration, count[slot] = launches.  returns #pairs
+int glrgtv_profile_read(float* ms, int* count, int n_slots) {
+    for (int i = 0; i < n_slots; ++i) { ms[i] = 0.f; count[i] = 0; }
+    int n = 0;
+    for (int i = 0; i < g_ev_used; ++i) {
+        float t = 0.f;
+        if (cudaEventSynchronize(g_ev[i][1]) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&t, g_ev[i][0], g_ev[i][1]) != cudaSuccess) continue;
+        if (g_ev_slot[i] < n_slots) { ms[g_ev_slot[i]] += t; count[g_ev_slot[i]] += 1; ++n; }
+    }
+    return n;
+}
 int glrgtv_abi_version(void) { return GLRGTV_ABI_VERSION; }
 const char* glrgtv_last_cuda_error(void) { return g_last_error; }
 int glrgtv_check_device(void) {

@@ -471,7 +471,9 @@ static int launch_bwd_stage(const BlockBwdArgs& a, void* stream) {
         configured = true;
     }
 #endif
+    GLR_PROF_BEGIN(GLRGTV_SLOT_BWD_X3 + MODE, stream);
     GLR_LAUNCH((k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW>), dim3((unsigned)blocks), GLR_BWD_THREADS, smem, stream, a);
+    GLR_PROF_END(GLRGTV_SLOT_BWD_X3 + MODE, stream);
     return GLR_CHECK_LAUNCH();
 }
 
@@ -543,12 +545,15 @@ extern "C" int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params
     sc.H /= 2; sc.W /= 2;
     const size_t C = (size_t)s->G * s->F, HW = (size_t)s->H * s->W, HWc = HW / 4;
     float* scr = ws + o_scr;
+    GLR_PROF_BEGIN(GLRGTV_SLOT_BWD_WEIGHTS, stream);
     if ((rc = glr_edge_weights_bwd_strided(s, &win, feat0, 2 * C * HW, p->gtv0.multiM, sv->wT0, a.gwT0, gfeat0,
                                            2 * C * HW, gr->gtv0_M, scr, stream))) return rc;
     if ((rc = glr_edge_weights_bwd_strided(s, &win, feat0 + C * HW, 2 * C * HW, p->glr0.multiM, sv->wL0, a.gwL0,
                                            gfeat0 + C * HW, 2 * C * HW, gr->glr0_M, scr, stream))) return rc;
     if ((rc = glr_edge_weights_bwd_strided(&sc, &win, feat1, 2 * C * HWc, p->gtv1.multiM, sv->wT1, a.gwT1, gfeat1,
                                            2 * C * HWc, gr->gtv1_M, scr, stream))) return rc;
-    return glr_edge_weights_bwd_strided(&sc, &win, feat1 + C * HWc, 2 * C * HWc, p->glr1.multiM, sv->wL1, a.gwL1,
-                                        gfeat1 + C * HWc, 2 * C * HWc, gr->glr1_M, scr, stream);
+    rc = glr_edge_weights_bwd_strided(&sc, &win, feat1 + C * HWc, 2 * C * HWc, p->glr1.multiM, sv->wL1, a.gwL1,
+                                      gfeat1 + C * HWc, 2 * C * HWc, gr->glr1_M, scr, stream);
+    GLR_PROF_END(GLRGTV_SLOT_BWD_WEIGHTS, stream);
+    return rc;
 }

@@ -237,7 +237,9 @@ static int launch_stage(const BlockFwdArgs& a, void* stream) {
         configured = true;
     }
 #endif
+    GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_BA + MODE, stream);
     GLR_LAUNCH((k_block_stage<MODE, GLR_TH, GLR_TW>), dim3((unsigned)blocks), GLR_THREADS, smem, stream, a);
+    GLR_PROF_END(GLRGTV_SLOT_FWD_BA + MODE, stream);
     return GLR_CHECK_LAUNCH();
 }
 
@@ -255,8 +257,10 @@ static int launch_weights(const glrgtv_shape& s, const float* feat, const float*
             return glr_record_launch_error();
     }
 #endif
+    GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_WEIGHTS, stream);
     GLR_LAUNCH((k_block_weights<GLR_WT_TH, GLR_WT_TW>), dim3((unsigned)blocks), GLR_THREADS, smem, stream, s, feat, Mt,
                Ml, wt, wl);
+    GLR_PROF_END(GLRGTV_SLOT_FWD_WEIGHTS, stream);
     return GLR_CHECK_LAUNCH();
 }
 

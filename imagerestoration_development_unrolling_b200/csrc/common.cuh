@@ -52,14 +52,22 @@ typedef void* cudaStream_t;
                 }                                                                      \
     } while (0)
 #define GLR_CHECK_LAUNCH() GLRGTV_OK
+#define GLR_PROF_BEGIN(slot, stream) ((void)0)
+#define GLR_PROF_END(slot, stream) ((void)0)
 static inline int glr_memset_async(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 #else
 // ------------------------------------------------------------------ CUDA build
 #include <cuda_runtime.h>
 #define GLR_SMEM_DECL(name) extern __shared__ __align__(16) float name[]
+extern unsigned long long g_glr_launches;  // kernels launched by this library (bench.py reports it)
 #define GLR_LAUNCH(kernel, grid, block, smem_bytes, stream, ...) \
-    kernel<<<(grid), (block), (smem_bytes), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+    (++g_glr_launches, kernel<<<(grid), (block), (smem_bytes), (cudaStream_t)(stream)>>>(__VA_ARGS__))
 int glr_record_launch_error(void);
+// optional per-kernel timing (glrgtv_profile_*): event pairs recorded on the launching stream
+void glr_prof_mark(int slot, int end, void* stream);
+extern int g_glr_prof_on;
+#define GLR_PROF_BEGIN(slot, stream) do { if (g_glr_prof_on) glr_prof_mark((slot), 0, (stream)); } while (0)
+#define GLR_PROF_END(slot, stream) do { if (g_glr_prof_on) glr_prof_mark((slot), 1, (stream)); } while (0)
 #define GLR_CHECK_LAUNCH() glr_record_launch_error()
 static inline int glr_memset_async(void* p, int v, size_t n, cudaStream_t s) {
     return cudaMemsetAsync(p, v, n, s) == cudaSuccess ? 0 : -1;

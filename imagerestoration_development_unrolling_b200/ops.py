@@ -316,3 +316,213 @@ def _(x):
 
 pool2.register_autograd(lambda ctx, g: unpool2(g))
 unpool2.register_autograd(lambda ctx, g: pool2(g))
+
+
+# ====================================================================== a2 / a3: normalise, gather
+@torch.library.custom_op(f"{_NS}::normalize_transform", mutates_args=())
+def normalize_transform(feat: Tensor, multiM: Tensor) -> Tensor:
+    _chk(feat, multiM)
+    feat, multiM = _c(feat), _c(multiM)
+    out = torch.empty_like(feat)
+    _call("glrgtv_normalize_fwd", feat, _shape5(feat), feat, multiM, out)
+    return out
+
+
+@normalize_transform.register_fake
+def _(feat, multiM):
+    return torch.empty_like(feat)
+
+
+@torch.library.custom_op(f"{_NS}::normalize_transform_bwd", mutates_args=())
+def normalize_transform_bwd(feat: Tensor, multiM: Tensor, g: Tensor) -> Tuple[Tensor, Tensor]:
+    _chk(feat, multiM, g)
+    feat, multiM, g = _c(feat), _c(multiM), _c(g)
+    gfeat, gM = torch.empty_like(feat), torch.zeros_like(multiM)
+    _call("glrgtv_normalize_bwd", feat, _shape5(feat), feat, multiM, g, gfeat, gM)
+    return gfeat, gM
+
+
+@normalize_transform_bwd.register_fake
+def _(feat, multiM, g):
+    return torch.empty_like(feat), torch.empty_like(multiM)
+
+
+normalize_transform.register_autograd(
+    lambda ctx, g: normalize_transform_bwd(*ctx.saved_tensors, g),
+    setup_context=lambda ctx, inputs, output: ctx.save_for_backward(*inputs))
+
+
+@torch.library.custom_op(f"{_NS}::gather_neighbors", mutates_args=())
+def gather_neighbors(x: Tensor, edges: List[int]) -> Tensor:
+    _chk(x)
+    x = _c(x)
+    B, G, F, H, W = x.shape
+    out = x.new_empty(B, G, F, len(edges) // 2, H, W)
+    _call("glrgtv_gather_neighbors_fwd", x, _shape5(x), _win(edges), x, out)
+    return out
+
+
+@gather_neighbors.register_fake
+def _(x, edges):
+    B, G, F, H, W = x.shape
+    return x.new_empty(B, G, F, len(edges) // 2, H, W)
+
+
+@torch.library.custom_op(f"{_NS}::gather_neighbors_bwd", mutates_args=())
+def gather_neighbors_bwd(g: Tensor, edges: List[int]) -> Tensor:
+    _chk(g)
+    g = _c(g)
+    B, G, F, E, H, W = g.shape
+    gx = g.new_empty(B, G, F, H, W)
+    _call("glrgtv_gather_neighbors_bwd", g, L.make_shape(B, G, F, H, W), _win(edges), g, gx)
+    return gx
+
+
+@gather_neighbors_bwd.register_fake
+def _(g, edges):
+    B, G, F, E, H, W = g.shape
+    return g.new_empty(B, G, F, H, W)
+
+
+def _gn_setup(ctx, inputs, output):
+    ctx.edges = inputs[1]
+
+
+gather_neighbors.register_autograd(lambda ctx, g: (gather_neighbors_bwd(g, ctx.edges), None), setup_context=_gn_setup)
+
+
+# ====================================================================== the fused block (hot path)
+# params layout: for each of GTVmodule00, GLRmodule00, GTVmodule01, GLRmodule01: p01, p02a, p02b, p03, multiM (20),
+# then alphaCGD, betaCGD, muys00, ro00, gamma00, muys01, ro01, gamma01 (8), then optionally skip_weight (1).
+_N_BLOCK_PARAMS = 28
+_SAVED = ("wT0", "wL0", "wT1", "wL1", "bA", "x1", "bB", "r1", "x2")
+
+
+def _block_structs(params: Sequence[Tensor]):
+    p = L.BlockParams()
+    for i, field in enumerate(("gtv0", "glr0", "gtv1", "glr1")):
+        op = getattr(p, field)
+        op.stats = L.make_stats(*params[5 * i:5 * i + 4])
+        op.multiM = params[5 * i + 4].data_ptr()
+    for j, field in enumerate(("alpha", "beta", "mu0", "ro0", "gamma0", "mu1", "ro1", "gamma1")):
+        setattr(p, field, params[20 + j].data_ptr())
+    p.skip = params[28].data_ptr() if len(params) > _N_BLOCK_PARAMS else None
+    return p
+
+
+def _block_geometry(x: Tensor, n_graphs: int):
+    B, C, H, W = x.shape
+    if C % n_graphs or H % 2 or W % 2:
+        raise RuntimeError(f"lowpass_block: C={C} must be a multiple of n_graphs={n_graphs} and H, W even (got {H}x{W})")
+    return B, n_graphs, C // n_graphs, H, W
+
+
+def _saved_shapes(B, G, F, H, W):
+    return [(B, G, 4, H, W)] * 2 + [(B, G, 4, H // 2, W // 2)] * 2 + [(B, G, F, H, W)] * 5
+
+
+@torch.library.custom_op(f"{_NS}::lowpass_block_fwd", mutates_args=())
+def lowpass_block_fwd(x: Tensor, feat0: Tensor, feat1: Tensor, params: Sequence[Tensor], n_graphs: int) -> List[Tensor]:
+    """-> [out, wT0, wL0, wT1, wL1, bA, x1, bB, r1, x2]   (glrgtv_block_fwd; 6 kernel launches)"""
+    _chk(x, feat0, feat1, *params)
+    if len(params) not in (_N_BLOCK_PARAMS, _N_BLOCK_PARAMS + 1):
+        raise RuntimeError("lowpass_block: expected 28 (+1 skip) parameter tensors")
+    x, feat0, feat1 = _c(x), _c(feat0), _c(feat1)
+    params = [_c(p) for p in params]
+    B, G, F, H, W = _block_geometry(x, n_graphs)
+    out = torch.empty_like(x)
+    saved = [x.new_empty(s) for s in _saved_shapes(B, G, F, H, W)]
+    sv = L.BlockSaved(*[t.data_ptr() for t in saved])
+    _call("glrgtv_block_fwd", x, L.make_shape(B, G, F, H, W), _block_structs(params), x, feat0, feat1, out, sv)
+    return [out] + saved
+
+
+@lowpass_block_fwd.register_fake
+def _(x, feat0, feat1, params, n_graphs):
+    B, C, H, W = x.shape
+    G, F = n_graphs, C // n_graphs
+    return [torch.empty_like(x)] + [x.new_empty(s) for s in _saved_shapes(B, G, F, H, W)]
+
+
+@torch.library.custom_op(f"{_NS}::lowpass_block_bwd", mutates_args=())
+def lowpass_block_bwd(x: Tensor, feat0: Tensor, feat1: Tensor, params: Sequence[Tensor], saved: Sequence[Tensor],
+                      gout: Tensor, n_graphs: int) -> List[Tensor]:
+    """-> [gx, gfeat0, gfeat1, flat parameter gradients]   (glrgtv_block_bwd; 12 kernel launches)"""
+    _chk(x, feat0, feat1, gout, *params, *saved)
+    x, feat0, feat1, gout = _c(x), _c(feat0), _c(feat1), _c(gout)
+    params = [_c(p) for p in params]
+    B, G, F, H, W = _block_geometry(x, n_graphs)
+    C = G * F
+    shp = L.make_shape(B, G, F, H, W)
+    has_skip = len(params) > _N_BLOCK_PARAMS
+    # one flat zeroed buffer for every parameter gradient (split into per-parameter views by the caller)
+    flat = x.new_zeros(sum(_grad_sizes(C, G, F)))
+    ptrs, o = [], 0
+    for n in _grad_sizes(C, G, F):
+        ptrs.append(flat.data_ptr() + 4 * o)
+        o += n
+    gr = L.BlockGrads(*ptrs)
+    if not has_skip:
+        gr.skip = None
+    nbytes = _lib().glrgtv_block_bwd_workspace_bytes(shp)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
+    gx, gf0, gf1 = torch.empty_like(x), torch.empty_like(feat0), torch.empty_like(feat1)
+    sv = L.BlockSaved(*[t.data_ptr() for t in saved])
+    _call("glrgtv_block_bwd", x, shp, _block_structs(params), x, feat0, feat1, sv, gout, gx, gf0, gf1, gr, ws, nbytes)
+    return [gx, gf0, gf1, flat]
+
+
+def _grad_sizes(C, G, F):
+    return [4 * C] * 4 + [G * F] * 4 + [3 * G] * 2 + [G] * 6 + [2]
+
+
+def _split_param_grads(flat: Tensor, params: Sequence[Tensor], G: int, F: int) -> List[Tensor]:
+    """flat gradient buffer of glrgtv_block_bwd -> one tensor per entry of the params layout"""
+    C = G * F
+    views, o = [], 0
+    for n in _grad_sizes(C, G, F):
+        views.append(flat[o:o + n])
+        o += n
+    out = []
+    for i in range(4):
+        out += [views[i][k * C:(k + 1) * C].reshape(params[5 * i + k].shape) for k in range(4)]
+        out.append(views[4 + i].reshape(G, F))
+    out += [views[8].reshape(3, G), views[9].reshape(3, G)] + [views[10 + j] for j in range(6)]
+    if len(params) > _N_BLOCK_PARAMS:
+        out.append(views[16])
+    return out
+
+
+@lowpass_block_bwd.register_fake
+def _(x, feat0, feat1, params, saved, gout, n_graphs):
+    G = n_graphs
+    F = x.shape[1] // G
+    return [torch.empty_like(x), torch.empty_like(feat0), torch.empty_like(feat1), x.new_empty(sum(_grad_sizes(G * F, G, F)))]
+
+
+def _lb_setup(ctx, inputs, output):
+    x, feat0, feat1, params, n_graphs = inputs
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(x, feat0, feat1, *params, *output[1:])
+    ctx.n_params = len(params)
+    ctx.n_graphs = n_graphs
+
+
+def _lb_backward(ctx, grads):
+    gout = grads[0]
+    t = ctx.saved_tensors
+    x, feat0, feat1 = t[:3]
+    params, saved = list(t[3:3 + ctx.n_params]), list(t[3 + ctx.n_params:])
+    if gout is None:
+        return None, None, None, [None] * ctx.n_params, None
+    res = lowpass_block_bwd(x, feat0, feat1, params, saved, gout, ctx.n_graphs)
+    G = ctx.n_graphs
+    return res[0], res[1], res[2], _split_param_grads(res[3], params, G, x.shape[1] // G), None
+
+
+lowpass_block_fwd.register_autograd(_lb_backward, setup_context=_lb_setup)
+
+
+def lowpass_block(x: Tensor, feat0: Tensor, feat1: Tensor, params: Sequence[Tensor], n_graphs: int) -> Tensor:
+    """LocalLowpassFilteringBlock / MixtureGTVGLR forward (V1X0:707-811, 985-988) as one differentiable op."""
+    return lowpass_block_fwd(x, feat0, feat1, list(params), n_graphs)[0]

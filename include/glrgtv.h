@@ -71,6 +71,22 @@ const char* glrgtv_last_cuda_error(void);
 /* 0 when the current CUDA device can run this library (compute capability 10.x) */
 int glrgtv_check_device(void);
 
+/* kernels launched by this library since it was loaded (bench.py's gpu_launches) */
+unsigned long long glrgtv_launch_count(void);
+
+/* Optional per-kernel timing of the fused block entry points: one CUDA-event pair is recorded on the
+ * launching stream around every kernel while enabled.  glrgtv_profile_read() waits for the events and
+ * returns, per slot (glrgtv_prof_slot), the summed duration in ms and the number of launches. */
+typedef enum glrgtv_prof_slot {
+    GLRGTV_SLOT_FWD_WEIGHTS = 0,
+    GLRGTV_SLOT_FWD_BA = 1, GLRGTV_SLOT_FWD_X1 = 2, GLRGTV_SLOT_FWD_X2 = 3, GLRGTV_SLOT_FWD_X3 = 4,
+    GLRGTV_SLOT_BWD_X3 = 5, GLRGTV_SLOT_BWD_X2 = 6, GLRGTV_SLOT_BWD_X1 = 7, GLRGTV_SLOT_BWD_BA = 8,
+    GLRGTV_SLOT_BWD_WEIGHTS = 9,
+    GLRGTV_SLOT_COUNT = 10
+} glrgtv_prof_slot;
+int glrgtv_profile_enable(int on);
+int glrgtv_profile_read(float* ms, int* count, int n_slots);
+
 /* ------------------------------------------------------------------------------------------------
  * Per-operator entry points (public methods of GLRFast / GTVFast)
  * ---------------------------------------------------------------------------------------------- */
@@ -189,10 +205,6 @@ int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params* p, const 
                      const float* feat0, const float* feat1, const glrgtv_block_saved* saved,
                      const float* gout, float* gx, float* gfeat0, float* gfeat1,
                      const glrgtv_block_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
-
-/* Host-buffer convenience for embedding without PyTorch: copies x/feat in, runs glrgtv_block_fwd on
- * `stream`, copies out back; all device memory comes from `workspace` (device, >= the size below). */
-size_t glrgtv_block_fwd_host_workspace_bytes(const glrgtv_shape* s);
 
 #ifdef __cplusplus
 }

@@ -88,9 +88,24 @@ def _idx(n: int, d: int, mode: str, device) -> torch.Tensor:
     raise ValueError(mode)
 
 
-def shift_clamp(x: torch.Tensor, dh: int, dw: int) -> torch.Tensor:
+def _shift_padded(x: torch.Tensor, dh: int, dw: int, mode: str) -> torch.Tensor:
+    # pad by |d| on the side the shift reads from, then take the H x W window that starts at the shift
     H, W = x.shape[-2:]
-    return x.index_select(-2, _idx(H, dh, "clamp", x.device)).index_select(-1, _idx(W, dw, "clamp", x.device))
+    if dh == 0 and dw == 0:
+        return x
+    pads = (max(-dw, 0), max(dw, 0), max(-dh, 0), max(dh, 0))
+    lead = x.shape[:-2]
+    xp = torch.nn.functional.pad(x.reshape(1, -1, H, W), pads, mode=mode)
+    h0, w0 = max(dh, 0), max(dw, 0)
+    return xp[..., h0:h0 + H, w0:w0 + W].reshape(*lead, H, W)
+
+
+def shift_clamp(x: torch.Tensor, dh: int, dw: int) -> torch.Tensor:
+    """x[cl(h+dh), cl(w+dw)]"""
+    H, W = x.shape[-2:]
+    if abs(dh) >= H or abs(dw) >= W:   # window wider than the image: fall back to explicit indices
+        return x.index_select(-2, _idx(H, dh, "clamp", x.device)).index_select(-1, _idx(W, dw, "clamp", x.device))
+    return _shift_padded(x, dh, dw, "replicate")
 
 
 def shift_reflect(x: torch.Tensor, dh: int, dw: int) -> torch.Tensor:

@@ -1,0 +1,151 @@
+"""The fused block (LocalLowpassFilteringBlock -> ops.lowpass_block -> glrgtv_block_fwd/bwd) on the GPU:
+against the committed golden vectors of the reference, against the oracle on seeded inputs, and - at the
+full benchmark sizes, where the CPU oracle is too slow - through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import glr_gtv_oracle as O
+from tests.util import rel, random_block_state
+
+pytestmark = pytest.mark.gpu
+TOL_OUT, TOL_GRAD = 1e-4, 1e-4      # BASELINE.json north_star: 1e-4 relative in fp32 (relative L2 norm)
+
+
+@pytest.fixture(scope="module")
+def M():
+    from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as m
+    return m
+
+
+def make_block(M, dim, G, sd):
+    blk = M.LocalLowpassFilteringBlock(dim=dim, nsubnets=1, ngraphs=G)
+    blk.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
+    return blk.cuda()
+
+
+def run_block(blk, x, gout):
+    xx = x.float().cuda().requires_grad_(True)
+    out = blk(xx)
+    names = [k for k, _ in blk.named_parameters()]
+    grads = torch.autograd.grad(out, [xx] + [p for _, p in blk.named_parameters()], gout.float().cuda())
+    return out, grads[0], dict(zip(names, grads[1:]))
+
+
+def check_against(out, gx, pg, ref_out, ref_gx, ref_pg):
+    assert rel(out, ref_out) < TOL_OUT, rel(out, ref_out)
+    assert rel(gx, ref_gx) < TOL_GRAD, rel(gx, ref_gx)
+    for k, r in ref_pg.items():
+        if float(r.abs().max()) == 0.0:
+            assert float(pg[k].abs().max()) == 0.0, k
+        else:
+            assert rel(pg[k], r) < 3 * TOL_GRAD, (k, rel(pg[k], r))
+
+
+@pytest.mark.parametrize("name", ["block_f6_g2", "block_f12_g2", "block_f6_g4_tiny"])
+def test_golden_reference_vectors(M, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    dim, G = int(g["meta"][0]), int(g["meta"][1])
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    blk = make_block(M, dim, G, sd)
+    out, gx, pg = run_block(blk, g["x"], g["gout"])
+    check_against(out, gx, pg, g["out"], g["gx"], {k[5:]: v for k, v in g.items() if k.startswith("grad.")})
+
+
+# shipped v13 geometries (F=6 / F=12, G up to 32), partial tiles, multi-tile
+@pytest.mark.parametrize("case", [(48, 8, 2, 64, 96), (96, 16, 1, 34, 66), (192, 16, 1, 32, 32), (384, 32, 1, 16, 16),
+                                  (24, 4, 3, 2, 2), (12, 2, 1, 70, 38)])
+def test_against_oracle(M, case):
+    dim, G, B, H, W = case
+    sd = random_block_state(dim, G, seed=dim + H)
+    gen = torch.Generator().manual_seed(7 * H + W)
+    x, gout = torch.randn(B, dim, H, W, generator=gen), torch.randn(B, dim, H, W, generator=gen)
+    ref = O.lowpass_block_fwd_bwd({k: v.double() for k, v in sd.items()}, x.double(), gout.double())
+    out, gx, pg = run_block(make_block(M, dim, G, sd), x, gout)
+    check_against(out, gx, pg, *ref)
+
+
+def composite_forward(blk, x):
+    """the same block out of the PER-OPERATOR kernels (an independent CUDA implementation of the path)"""
+    lf = blk.local_filter
+    B, C, H, W = x.shape
+    G, F = lf.n_graphs, lf.n_node_fts
+    v5 = lambda t: t.reshape(B, G, F, t.shape[-2], t.shape[-1])
+    f0, f1 = lf.patchs_features_extraction00(x), lf.patchs_features_extraction01(x)
+    wT0, wL0 = lf.GTVmodule00.extract_edge_weights(v5(f0[:, :C])), lf.GLRmodule00.extract_edge_weights(v5(f0[:, C:]))
+    wT1, wL1 = lf.GTVmodule01.extract_edge_weights(v5(f1[:, :C])), lf.GLRmodule01.extract_edge_weights(v5(f1[:, C:]))
+    from imagerestoration_development_unrolling_b200 import ops
+    bc = lambda v: torch.exp(v)[None, :, None, None, None]
+    A = lambda z: lf.apply_lightweight_transformer(z, [wT0, wT1], [wL0, wL1])
+    y = v5(x)
+    R = lambda z, thr: (bc(lf.ro00) * lf.GTVmodule00.op_C_transpose(thr(lf.GTVmodule00.op_C(z, *wT0), lf.gamma00), *wT0)
+                        + ops.unpool2(bc(lf.ro01) * lf.GTVmodule01.op_C_transpose(thr(lf.GTVmodule01.op_C(ops.pool2(z), *wT1), lf.gamma01), *wT1)))
+    ident = lambda t, gamma: t
+    phi = lambda t, gamma: 2 * lf.soft_threshold(t, torch.exp(gamma)) - t
+    a, be = lf.alphaCGD[:, None, :, None, None, None], lf.betaCGD[:, None, :, None, None, None]
+    bA = y + R(y, ident)
+    x1 = bA + a[0] * (bA - A(bA))
+    bB = y + R(x1, phi)
+    r1 = bB - A(x1)
+    x2 = x1 + a[1] * r1
+    u2 = (bB - A(x2)) + be[2] * r1
+    x3 = x2 + a[2] * u2
+    return blk.skip_weight[0] * x + blk.skip_weight[1] * x3.reshape(B, C, H, W)
+
+
+def test_fused_equals_per_operator_path_with_gradients(M):
+    dim, G, B, H, W = 48, 8, 2, 96, 64
+    sd = random_block_state(dim, G, seed=5)
+    blk = make_block(M, dim, G, sd)
+    gen = torch.Generator().manual_seed(1)
+    x, gout = torch.randn(B, dim, H, W, generator=gen), torch.randn(B, dim, H, W, generator=gen)
+    out, gx, pg = run_block(blk, x, gout)
+    xx = x.cuda().requires_grad_(True)
+    out2 = composite_forward(blk, xx)
+    names = [k for k, _ in blk.named_parameters()]
+    grads = torch.autograd.grad(out2, [xx] + [p for _, p in blk.named_parameters()], gout.cuda())
+    check_against(out, gx, pg, out2, grads[0], {k: g for k, g in zip(names, grads[1:]) if k != "local_filter.betaCGD"})
+
+
+@pytest.mark.parametrize("scale", [0, 1, 2, 3])
+def test_full_benchmark_size_properties(M, scale):
+    """BASELINE config 2 shapes (batch 32, 256x256 input): [32,48,256,256] ... [32,384,32,32].
+    Properties: (1) fused forward == per-operator forward; (2) batch items are independent: a permuted batch
+    gives the permuted result bit-for-bit; (3) a crop far from its border reproduces the full-image result
+    (receptive radius 25 at the block's own scale)."""
+    dim, G = [48, 96, 192, 384][scale], [8, 16, 16, 32][scale]
+    H = W = 256 >> scale
+    B = 32 if scale > 0 else 8          # the per-operator path materialises [B,G,F,E,H,W]; keep it bounded
+    sd = random_block_state(dim, G, seed=scale)
+    blk = make_block(M, dim, G, sd)
+    x = torch.randn(B, dim, H, W, generator=torch.Generator().manual_seed(scale)).cuda()
+    with torch.no_grad():
+        out = blk(x)
+        assert rel(out, composite_forward(blk, x)) < 2e-5
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(3)).cuda()
+        assert torch.equal(blk(x[perm].contiguous()), out[perm])
+        if H >= 128:
+            crop = blk(x[:2, :, 32:32 + 96, 64:64 + 96].contiguous())
+            assert rel(crop[:, :, 26:-26, 26:-26], out[:2, :, 32 + 26:32 + 96 - 26, 64 + 26:64 + 96 - 26]) < 1e-6
+    assert torch.isfinite(out).all()
+
+
+def test_state_dict_layout_matches_reference(M, golden_dir):
+    z = np.load(os.path.join(golden_dir, "block_f6_g2.npz"))
+    ref_keys = [k[3:] for k in z.files if k.startswith("sd.")]
+    blk = M.LocalLowpassFilteringBlock(dim=12, nsubnets=1, ngraphs=2)
+    assert list(blk.state_dict().keys()) == ref_keys            # names AND registration order
+    for k, v in blk.state_dict().items():
+        assert tuple(v.shape) == tuple(z["sd." + k].shape), k
+
+
+def test_default_init_matches_reference_values(M):
+    blk = M.LocalLowpassFilteringBlock(dim=12, nsubnets=1, ngraphs=2)
+    lf = blk.local_filter
+    assert torch.allclose(lf.muys00, torch.full((2,), float(np.log(np.float32(1e-3)))))
+    assert torch.allclose(lf.muys01, torch.full((2,), float(np.log(np.float32(1e-4)))))
+    assert torch.allclose(lf.alphaCGD, torch.full((3, 2), 0.5)) and torch.allclose(lf.betaCGD, torch.full((3, 2), 0.1))
+    assert float(lf.GTVmodule00.multiM[0, 0]) == 1.0 and float(lf.GLRmodule01.stats_kernel_p02a[0]) == 0.5

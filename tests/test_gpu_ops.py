@@ -1,0 +1,127 @@
+"""Per-operator CUDA kernels (through ops.py -> C ABI) against the oracle and its autograd, on the GPU."""
+import pytest
+import torch
+
+from oracle import glr_gtv_oracle as O
+
+pytestmark = pytest.mark.gpu
+WINDOWS = ["cross3", "full3", "small5", "full5"]
+SHAPES = [(2, 2, 3, 5, 7), (1, 3, 6, 2, 2), (1, 1, 4, 1, 6), (2, 4, 6, 33, 47), (1, 2, 12, 64, 96)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from imagerestoration_development_unrolling_b200 import ops as o
+    return o
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def rnd(*s, seed=0):
+    return torch.randn(*s, generator=torch.Generator().manual_seed(seed + sum(s)), dtype=torch.float64)
+
+
+def leaf(t):
+    return t.float().cuda().requires_grad_(True)
+
+
+@pytest.mark.parametrize("window", WINDOWS)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_edge_weights(ops, window, shape):
+    B, G, F, H, W = shape
+    edges = O.window_edges(window)
+    feat, M = rnd(B, G, F, H, W).requires_grad_(True), (1 + 0.5 * rnd(G, F)).requires_grad_(True)
+    gw = rnd(B, G, len(edges), H, W, seed=1)
+    ref = O.edge_weights(feat, M, edges)
+    gf_r, gM_r = torch.autograd.grad(ref, [feat, M], gw)
+    f, m = leaf(feat), leaf(M)
+    w = ops.edge_weights(f, m, ops.flat_edges(edges))
+    gf, gM = torch.autograd.grad(w, [f, m], gw.float().cuda())
+    assert rel(w, ref) < 2e-6 and rel(gf, gf_r) < 2e-5 and rel(gM, gM_r) < 2e-5
+
+
+@pytest.mark.parametrize("pad", [0, 1])
+@pytest.mark.parametrize("n_is_C", [True, False])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_stats_conv(ops, pad, n_is_C, shape):
+    B, G, F, H, W = shape
+    if pad == 1 and (H < 2 or W < 2):
+        pytest.skip("reflect needs >= 2 pixels")
+    n = G * F if n_is_C else 1
+    ps = [(torch.full((n, 1, 1, 1), v, dtype=torch.float64) + 0.2 * rnd(n, 1, 1, 1, seed=i)).requires_grad_(True)
+          for i, v in enumerate((1.0, 0.5, 0.5, 0.5))]
+    x, g = rnd(B, G, F, H, W).requires_grad_(True), rnd(B, G, F, H, W, seed=3)
+    for op, ref_fn in ((ops.stats_conv, lambda: O.stats_conv(x, ps, "clamp" if pad == 0 else "reflect")),
+                       (ops.stats_conv_t, lambda: O.stats_conv_transpose(x, ps))):
+        ref = ref_fn()
+        gr = torch.autograd.grad(ref, [x] + ps, g)
+        xs, pc = leaf(x), [leaf(p) for p in ps]
+        out = op(xs, *pc, pad)
+        gg = torch.autograd.grad(out, [xs] + pc, g.float().cuda())
+        assert rel(out, ref) < 1e-6
+        for a, b in zip(gg, gr):
+            assert rel(a, b) < 3e-5
+
+
+@pytest.mark.parametrize("window", WINDOWS)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_L_C_Ct(ops, window, shape):
+    B, G, F, H, W = shape
+    edges = O.window_edges(window)
+    E, fe = len(edges), ops.flat_edges(edges)
+    x = rnd(B, G, F, H, W).requires_grad_(True)
+    w = torch.softmax(rnd(B, G, E, H, W, seed=1), dim=2).detach().requires_grad_(True)
+    z = rnd(B, G, F, E, H, W, seed=2).requires_grad_(True)
+    g5, g6 = rnd(B, G, F, H, W, seed=3), rnd(B, G, F, E, H, W, seed=4)
+    for op, ref, a, g in ((ops.op_L, O.op_L(x, w, edges), x, g5), (ops.op_C, O.op_C_core(x, w, edges), x, g6),
+                          (ops.op_Ct, O.op_Ct_core(z, w, edges), z, g5)):
+        gr = torch.autograd.grad(ref, [a, w], g)
+        ac, wc = leaf(a), leaf(w)
+        out = op(ac, wc, fe)
+        gg = torch.autograd.grad(out, [ac, wc], g.float().cuda())
+        assert rel(out, ref) < 1e-6 and rel(gg[0], gr[0]) < 1e-6 and rel(gg[1], gr[1]) < 2e-6
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_soft_pool_normalize_gather(ops, shape):
+    B, G, F, H, W = shape
+    t, thr = rnd(B, G, F, 4, H, W).requires_grad_(True), (0.2 + torch.rand(G, dtype=torch.float64)).requires_grad_(True)
+    g = rnd(B, G, F, 4, H, W, seed=5)
+    ref = O.soft_threshold(t, thr)
+    gr = torch.autograd.grad(ref, [t, thr], g)
+    tc, hc = leaf(t), leaf(thr)
+    out = ops.soft_threshold(tc, hc)
+    gg = torch.autograd.grad(out, [tc, hc], g.float().cuda())
+    assert rel(out, ref) < 1e-6 and rel(gg[0], gr[0]) < 1e-6 and rel(gg[1], gr[1]) < 1e-4
+    # normalise
+    feat, M = rnd(B, G, F, H, W).requires_grad_(True), (1 + 0.5 * rnd(G, F)).requires_grad_(True)
+    ref = O.normalize_transform(feat, M)
+    gr = torch.autograd.grad(ref, [feat, M], rnd(B, G, F, H, W, seed=6))
+    fc, mc = leaf(feat), leaf(M)
+    out = ops.normalize_transform(fc, mc)
+    gg = torch.autograd.grad(out, [fc, mc], rnd(B, G, F, H, W, seed=6).float().cuda())
+    assert rel(out, ref) < 1e-6 and rel(gg[0], gr[0]) < 1e-5 and rel(gg[1], gr[1]) < 1e-5
+    # gather
+    edges = O.window_edges("small5")
+    x = rnd(B, G, F, H, W).requires_grad_(True)
+    ref = torch.stack([O.shift_clamp(x, dh, dw) for dh, dw in edges], dim=3)
+    gg6 = rnd(B, G, F, len(edges), H, W, seed=7)
+    gr = torch.autograd.grad(ref, x, gg6)[0]
+    xc = leaf(x)
+    out = ops.gather_neighbors(xc, ops.flat_edges(edges))
+    assert torch.equal(out.cpu().double(), ref.detach().float().double())
+    assert rel(torch.autograd.grad(out, xc, gg6.float().cuda())[0], gr) < 1e-6
+    if H % 2 == 0 and W % 2 == 0:
+        xc = leaf(x)
+        c = ops.pool2(xc)
+        assert rel(c, O.pool2(x)) < 1e-6
+        assert rel(torch.autograd.grad(c, xc, torch.ones_like(c))[0], 0.25 * torch.ones_like(x)) < 1e-7
+        assert rel(ops.unpool2(c), O.unpool2(O.pool2(x))) < 1e-6
+
+
+def test_cpu_tensors_are_refused(ops):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.pool2(torch.zeros(1, 1, 1, 2, 2))
