@@ -3,7 +3,7 @@
 
 #ifdef GLRGTV_EMU
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
-static thread_local float emu_smem_storage[64 * 1024];
+alignas(64) static thread_local float emu_smem_storage[64 * 1024];
 thread_local float* emu_smem = emu_smem_storage;
 extern "C" {
 int glrgtv_abi_version(void) { return GLRGTV_ABI_VERSION; }

@@ -5,8 +5,9 @@
 // runs the adjoint chain on the incoming gradient, and emits
 //   - the gradient wrt z                                  (one tensor write),
 //   - this stage's contribution to the four edge-weight gradients (accumulated over the graph's F
-//     channels in shared memory, then one read-modify-write per tile),
-//   - per-channel stats_kernel_p* gradients and per-graph scalar gradients (block reduction + atomics).
+//     channels in registers, then one read-modify-write per tile),
+//   - per-channel stats_kernel_p* gradients and per-graph scalar gradients (warp shuffles + shared atomics,
+//     then one global atomic per value and CTA).
 //
 //   BWD_X3:  gout, x2, bB, r1, x      -> gx2                 (r2 = bB - A x2, u2, x3 recomputed)
 //   BWD_X2:  gout, gx2, x1, r1        -> gx1                 (through r1 = bB - A x1 and bB = y + R_thr x1)
@@ -37,411 +38,598 @@ struct BlockBwdArgs {
     float* gz_out;
 };
 
-template <int TH, int TW>
-struct BwdSmem {
-    static constexpr int r4(int n) { return (n + 3) & ~3; }
-    static constexpr int F12 = r4((TH + 12) * (TW + 12)), F4 = r4((TH + 4) * (TW + 4)), F2 = r4((TH + 2) * (TW + 2)),
-                         F0 = r4(TH * TW);
-    static constexpr int C6 = r4((TH / 2 + 6) * (TW / 2 + 6)), C4 = r4((TH / 2 + 4) * (TW / 2 + 4)),
-                         C2 = r4((TH / 2 + 2) * (TW / 2 + 2)), C0 = r4((TH / 2) * (TW / 2));
-    // zf,gA,gB | sA,sB,gl,goA,goB | lA,oB,oT,gsL,gsT | pz,gcA,gcB | sA1,sB1,gl1,goA1,goB1 | lA1,oB1,oT1,gsL1,gsT1 |
-    // gzc | weights | gw accumulators | reduction scratch
-    static constexpr int value = 3 * F12 + 5 * F4 + 5 * F2 + 3 * C6 + 5 * C4 + 5 * C2 + C0 + 8 * F4 + 8 * C4 +
-                                 8 * F0 + 8 * C0 + 32 * 16 + 16;
+// shared-memory layout (floats) of one backward stage
+template <int MODE, int TH, int TW>
+struct BwdLayout {
+    using GF = Geo<TH, TW>;
+    using GC = Geo<TH / 2, TW / 2>;
+    static constexpr bool HAS_A = MODE != BWD_BA, HAS_R = MODE == BWD_X2 || MODE == BWD_BA, THR = MODE == BWD_X2;
+    static constexpr int F6 = GF::floats(6), F2 = GF::floats(2), F1 = GF::floats(1);
+    static constexpr int C3 = GC::floats(3), C2 = GC::floats(2), C1 = GC::floats(1);
+    static constexpr int zf = 0;
+    static constexpr int gA = zf + F6;
+    static constexpr int gB = gA + (HAS_A ? F6 : 0);
+    static constexpr int sA = gB + (HAS_R ? F6 : 0);
+    static constexpr int sB = sA + (HAS_A ? F2 : 0);
+    static constexpr int gl = sB + F2;
+    static constexpr int goA = gl + (HAS_A ? F2 : 0);
+    static constexpr int goB = goA + (HAS_A ? F2 : 0);
+    static constexpr int lA = goB + (HAS_R ? F2 : 0);
+    static constexpr int oB = lA + (HAS_A ? F1 : 0);
+    static constexpr int oT = oB + F1;
+    static constexpr int gsL = oT + (THR ? F1 : 0);
+    static constexpr int gsT = gsL + (HAS_A ? F1 : 0);
+    static constexpr int pz = gsT + F1;
+    static constexpr int gcA = pz + C3;
+    static constexpr int gcB = gcA + (HAS_A ? C3 : 0);
+    static constexpr int sA1 = gcB + (HAS_R ? C3 : 0);
+    static constexpr int sB1 = sA1 + (HAS_A ? C2 : 0);
+    static constexpr int gl1 = sB1 + C2;
+    static constexpr int goA1 = gl1 + (HAS_A ? C2 : 0);
+    static constexpr int goB1 = goA1 + (HAS_A ? C2 : 0);
+    static constexpr int lA1 = goB1 + (HAS_R ? C2 : 0);
+    static constexpr int oB1 = lA1 + (HAS_A ? C1 : 0);
+    static constexpr int oT1 = oB1 + C1;
+    static constexpr int gsL1 = oT1 + (THR ? C1 : 0);
+    static constexpr int gsT1 = gsL1 + (HAS_A ? C1 : 0);
+    // weights: raw wL (the L adjoint reads the neighbours' weights -> halo 2); GTV: coefficient planes, or the
+    // raw planes where the thresholded core needs them (then the linear core uses the raw planes too)
+    static constexpr int wL0 = gsT1 + C1;
+    static constexpr int cR0 = wL0 + (HAS_A ? 4 * F2 : 0);
+    static constexpr int cD0 = cR0 + (THR ? 0 : F2);
+    static constexpr int wT0 = cD0 + (THR ? 0 : F2);
+    static constexpr int wL1 = wT0 + (THR ? 4 * F2 : 0);
+    static constexpr int cR1 = wL1 + (HAS_A ? 4 * C2 : 0);
+    static constexpr int cD1 = cR1 + (THR ? 0 : C2);
+    static constexpr int wT1 = cD1 + (THR ? 0 : C2);
+    static constexpr int red = wT1 + (THR ? 4 * C2 : 0);
+    static constexpr int total = red + 64;
 };
 
-// accumulate the 5 tap products of one (upstream, operand) pair into the four stats-parameter sums
-__device__ __forceinline__ void stats_acc(float (&acc)[4], float ac, float ar, float ad, float au, float al) {
+// per-thread accumulators that live across the channel loop: on the GPU every thread owns at most ONE
+// epilogue quad, so a plain register array is enough; the emulation build (one thread per block) keeps one
+// slot per quad in static storage.
+#ifdef GLRGTV_EMU
+#define ACC_DECL(name, items, n) static thread_local float name##_store[(items) * (n)]
+#define ACC_PTR(name, i, n) (name##_store + (i) * (n))
+#define EPI_LOOP(i, n, first) for (int i = 0; i < (n); ++i)
+#else
+// a thread is either a fine-quad owner or a coarse-quad owner, never both: one register array serves both roles
+#define ACC_DECL(name, items, n)
+#define ACC_PTR(name, i, n) (acc_regs)
+#define EPI_LOOP(i, n, first) for (int i = (int)threadIdx.x - (first); i >= 0 && i < (n); i += (1 << 20))
+#endif
+
+// the four stats-parameter sums from five tap products
+__device__ __forceinline__ void stats_acc(float* acc, float ac, float ar, float ad, float au, float al) {
     acc[0] += ac;
     acc[1] += ar - ac;
     acc[2] += ad - ac;
     acc[3] += 4.f * ac - ar - ad - au - al;
 }
-// g[q] * y[q - o_t] for the five taps (y zero-extended)  -> St parameter gradient
-__device__ __forceinline__ void stats_acc_St(float (&acc)[4], float g, const View& y, int h, int w) {
-    const float* c = &y.at(h, w);
-    stats_acc(acc, g * c[0], g * c[-1], g * c[-y.nw], g * c[y.nw], g * c[1]);
-}
-// gs[p] * z[p + o_t] (z clamp-extended) -> S parameter gradient
-__device__ __forceinline__ void stats_acc_S(float (&acc)[4], float gs, const View& z, int h, int w) {
-    const float* c = &z.at(h, w);
-    stats_acc(acc, gs * c[0], gs * c[1], gs * c[z.nw], gs * c[-z.nw], gs * c[-1]);
-}
 
-// edge-weight gradient contributions of one pixel's four outgoing edges.
-//   L     : gw_e -= gl * s[n_e]
-//   GTV   : gw_e += D phi(t) + D w phi'(t) d,   D = go[p]-go[n], d = s[p]-s[n], t = w d  (linear: 2 w D d)
-// also returns the d/dGamma sum for the thresholded case.
-template <bool THR>
-__device__ __forceinline__ float gtv_edge_grads(float* acc, int stride, const View& go, const View& s, const WViews& w,
-                                                float G, int h, int x) {
-    const float* cg = &go.at(h, x);
-    const float* cs = &s.at(h, x);
-    const int og[4] = {-go.nw, -1, 1, go.nw}, os[4] = {-s.nw, -1, 1, s.nw};
-    float dG = 0.f;
+// Parameter-gradient work of one epilogue quad at one resolution (fine: z halo 6, coarse: z halo 3).
+//   st   : [T: p01,p02a,p02b,p03 | L: ...]  per-channel stats sums of this resolution's two modules
+//   sums : [mu, ro, gamma]                  per-graph sums of this resolution
+//   acc  : [L e0..e3][4] then [T e0..e3][4] edge-weight gradient accumulators of this quad
+// returns the forward St values (glr, gtv_lin) and the S-adjoint values VT+VL in V.
+template <int MODE, class G, int RZ>
+struct QuadWork {
+    static constexpr bool HAS_A = MODE != BWD_BA, HAS_R = MODE == BWD_X2 || MODE == BWD_BA, THR = MODE == BWD_X2;
+    static constexpr int P = G::P;
+    const G& g;
+    Plane<G, RZ> z;
+    Plane<G, 2> sA, sB, gl, goA, goB;
+    Plane<G, 1> lA, oB, oT, gsL, gsT;
+    const float* wT_global;  // raw GTV weights of this graph at this resolution, [4][H*W]
+    StatsTaps kT, kL;
+    float aT, aL, Gam;
+
+    // r = row within the tile, c = local column of the quad; ga/gb = upstream quads (loaded by the caller)
+    __device__ __forceinline__ void run(int r, int c, const float (&ga)[4], const float (&gb)[4], float* st, float* sums,
+                                        float* acc, float (&V)[4], float (&glr)[4], float (&gtv_lin)[4]) const {
+        const int h = g.h0 + r, w = g.gw(c);
+        N5 n;
+        float gtv_R[4];
+        // ---- GTV: forward value, St gradient, S adjoint + S gradient
+        ld_n5<P>(oB.lrc(r + 1, c), n);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        float we = w.e[e].at(h, x);
-        float D = cg[0] - cg[og[e]], d = cs[0] - cs[os[e]];
+        for (int j = 0; j < 4; ++j) {
+            gtv_lin[j] = kT.kc * n.c[j] + kT.kr * n.L(j) + kT.kd * n.u[j] + kT.ku * n.d[j] + kT.kl * n.Rr(j);
+            const float gu = aT * ((HAS_A ? ga[j] : 0.f) + (HAS_R && !THR ? gb[j] : 0.f));
+            stats_acc(st, gu * n.c[j], gu * n.L(j), gu * n.u[j], gu * n.d[j], gu * n.Rr(j));
+            gtv_R[j] = gtv_lin[j];
+        }
         if (THR) {
-            float t = we * d;
-            acc[e * stride] += D * glr_phi(t, G) + D * we * glr_dphi(t, G) * d;
-            if (fabsf(t) > G) dG += D * we * (t > 0.f ? -2.f : 2.f);
+            ld_n5<P>(oT.lrc(r + 1, c), n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                gtv_R[j] = kT.kc * n.c[j] + kT.kr * n.L(j) + kT.kd * n.u[j] + kT.ku * n.d[j] + kT.kl * n.Rr(j);
+                const float gu = aT * gb[j];
+                stats_acc(st, gu * n.c[j], gu * n.L(j), gu * n.u[j], gu * n.d[j], gu * n.Rr(j));
+            }
+        }
+        N5 nz;
+        ld_n5<P>(z.lrc(r + RZ, c), nz);
+        ld_n5<P>(gsT.lrc(r + 1, c), n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float self = 0.f;
+            if (w + j == g.W - 1) self += kT.kr;
+            if (h == g.H - 1) self += kT.kd;
+            if (h == 0) self += kT.ku;
+            if (w + j == 0) self += kT.kl;
+            V[j] = (kT.kc + self) * n.c[j] + kT.kr * n.L(j) + kT.kd * n.u[j] + kT.ku * n.d[j] + kT.kl * n.Rr(j);
+            const float gs = n.c[j];
+            stats_acc(st, gs * nz.c[j], gs * nz.Rr(j), gs * nz.d[j], gs * nz.u[j], gs * nz.L(j));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (HAS_A) sums[1] += aT * ga[j] * gtv_lin[j];
+            if (HAS_R) sums[1] += aT * gb[j] * gtv_R[j];
+        }
+        // ---- GLR
+        if (HAS_A) {
+            ld_n5<P>(lA.lrc(r + 1, c), n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                glr[j] = kL.kc * n.c[j] + kL.kr * n.L(j) + kL.kd * n.u[j] + kL.ku * n.d[j] + kL.kl * n.Rr(j);
+                const float gu = aL * ga[j];
+                stats_acc(st + 4, gu * n.c[j], gu * n.L(j), gu * n.u[j], gu * n.d[j], gu * n.Rr(j));
+                sums[0] += gu * glr[j];
+            }
+            ld_n5<P>(gsL.lrc(r + 1, c), n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float self = 0.f;
+                if (w + j == g.W - 1) self += kL.kr;
+                if (h == g.H - 1) self += kL.kd;
+                if (h == 0) self += kL.ku;
+                if (w + j == 0) self += kL.kl;
+                V[j] += (kL.kc + self) * n.c[j] + kL.kr * n.L(j) + kL.kd * n.u[j] + kL.ku * n.d[j] + kL.kl * n.Rr(j);
+                const float gs = n.c[j];
+                stats_acc(st + 4, gs * nz.c[j], gs * nz.Rr(j), gs * nz.d[j], gs * nz.u[j], gs * nz.L(j));
+            }
+            // edge weights of L: gw_e -= gl * sA[n_e]
+            float glq[4];
+            ld4(gl.lrc(r + 2, c), glq);
+            ld_n5<P>(sA.lrc(r + 2, c), n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[0 * 4 + j] -= glq[j] * n.u[j];
+                acc[1 * 4 + j] -= glq[j] * n.L(j);
+                acc[2 * 4 + j] -= glq[j] * n.Rr(j);
+                acc[3 * 4 + j] -= glq[j] * n.d[j];
+            }
         } else {
-            acc[e * stride] += 2.f * we * D * d;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) glr[j] = 0.f;
+        }
+        // ---- edge weights of GTV: gw_e += D phi(t) + D w phi'(t) d  (linear: 2 w D d), D = go[p]-go[n], d = s[p]-s[n]
+        float we[4][4];
+        const size_t HW = (size_t)g.H * g.W, o = (size_t)h * g.W + w;
+        const bool full = (g.W & 3) == 0 && g.quad_inside(h, w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (full) ld4(wT_global + e * HW + o, we[e]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) we[e][j] = g.inside(h, w + j) ? wT_global[e * HW + o + j] : 0.f;
+            }
+        }
+        N5 ns;
+        ld_n5<P>(sB.lrc(r + 2, c), ns);
+        float* accT = acc + 16;
+        if (HAS_A) {
+            ld_n5<P>(goA.lrc(r + 2, c), n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                accT[0 * 4 + j] += 2.f * we[0][j] * (n.c[j] - n.u[j]) * (ns.c[j] - ns.u[j]);
+                accT[1 * 4 + j] += 2.f * we[1][j] * (n.c[j] - n.L(j)) * (ns.c[j] - ns.L(j));
+                accT[2 * 4 + j] += 2.f * we[2][j] * (n.c[j] - n.Rr(j)) * (ns.c[j] - ns.Rr(j));
+                accT[3 * 4 + j] += 2.f * we[3][j] * (n.c[j] - n.d[j]) * (ns.c[j] - ns.d[j]);
+            }
+        }
+        if (HAS_R) {
+            ld_n5<P>(goB.lrc(r + 2, c), n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float D[4] = {n.c[j] - n.u[j], n.c[j] - n.L(j), n.c[j] - n.Rr(j), n.c[j] - n.d[j]};
+                const float d[4] = {ns.c[j] - ns.u[j], ns.c[j] - ns.L(j), ns.c[j] - ns.Rr(j), ns.c[j] - ns.d[j]};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (THR) {
+                        const float t = we[e][j] * d[e];
+                        accT[e * 4 + j] += D[e] * glr_phi(t, Gam) + D[e] * we[e][j] * glr_dphi(t, Gam) * d[e];
+                        if (fabsf(t) > Gam) sums[2] += D[e] * we[e][j] * (t > 0.f ? -2.f : 2.f);
+                    } else {
+                        accT[e * 4 + j] += 2.f * we[e][j] * D[e] * d[e];
+                    }
+                }
+            }
         }
     }
-    return dG;
+};
+
+// warp-reduce N values and add lane 0's totals into shared accumulators
+template <int N>
+__device__ __forceinline__ void warp_commit(float* vals, float* sh) {
+#ifdef GLRGTV_EMU
+    for (int k = 0; k < N; ++k) sh[k] += vals[k];
+#else
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        float v = vals[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(&sh[k], v);
+    }
+#endif
 }
 
-template <int MODE, int TH, int TW>
-__global__ void __launch_bounds__(512) k_block_bwd_stage(BlockBwdArgs a) {
+template <int MODE, int TH, int TW, int NT>
+__global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
     GLR_SMEM_DECL(smem);
-    constexpr bool HAS_A = MODE != BWD_BA;                  // adjoint of A(.) (GLR + linear GTV) on gA
-    constexpr bool HAS_R = MODE == BWD_X2 || MODE == BWD_BA;  // adjoint of R(.) on gB
-    constexpr bool THR = MODE == BWD_X2;                    // R is the thresholded one
-    const int H = a.s.H, W = a.s.W, Hc = H / 2, Wc = W / 2, F = a.s.F, G = a.s.G;
+    using LY = BwdLayout<MODE, TH, TW>;
+    using GF = typename LY::GF;
+    using GC = typename LY::GC;
+    constexpr bool HAS_A = LY::HAS_A, HAS_R = LY::HAS_R, THR = LY::THR;
+    constexpr int NQF = GF::items(0), NQC = GC::items(0);   // epilogue quads: fine / coarse
+    static_assert(NT >= NQF + NQC, "one epilogue quad per thread");
+    const int H = a.s.H, W = a.s.W, F = a.s.F, G = a.s.G;
     const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
     const int tile = blockIdx.x % (tiles_w * tiles_h), plane = blockIdx.x / (tiles_w * tiles_h);
     const int g = plane % G, b = plane / G;
-    const int h0 = (tile / tiles_w) * TH, w0 = (tile % tiles_w) * TW, hc0 = h0 / 2, wc0 = w0 / 2;
-    const size_t HW = (size_t)H * W, HWc = (size_t)Hc * Wc;
+    GF gf; gf.H = H; gf.W = W; gf.h0 = (tile / tiles_w) * TH; gf.w0 = (tile % tiles_w) * TW;
+    GC gc; gc.H = H / 2; gc.W = W / 2; gc.h0 = gf.h0 / 2; gc.w0 = gf.w0 / 2;
+    const size_t HW = (size_t)H * W, HWc = HW / 4;
+    const bool vec = (W & 3) == 0, vecc = (gc.W & 3) == 0;
 
-    // ---- shared memory
-    float* cur = smem;
-    View zf = make_view(cur, h0 - 6, w0 - 6, TH + 12, TW + 12);
-    View gA = make_view(cur, h0 - 6, w0 - 6, TH + 12, TW + 12);
-    View gB = make_view(cur, h0 - 6, w0 - 6, TH + 12, TW + 12);
-    View sA = make_view(cur, h0 - 2, w0 - 2, TH + 4, TW + 4);
-    View sB = make_view(cur, h0 - 2, w0 - 2, TH + 4, TW + 4);
-    View gl = make_view(cur, h0 - 2, w0 - 2, TH + 4, TW + 4);
-    View goA = make_view(cur, h0 - 2, w0 - 2, TH + 4, TW + 4);
-    View goB = make_view(cur, h0 - 2, w0 - 2, TH + 4, TW + 4);
-    View lA = make_view(cur, h0 - 1, w0 - 1, TH + 2, TW + 2);
-    View oB = make_view(cur, h0 - 1, w0 - 1, TH + 2, TW + 2);
-    View oT = make_view(cur, h0 - 1, w0 - 1, TH + 2, TW + 2);
-    View gsL = make_view(cur, h0 - 1, w0 - 1, TH + 2, TW + 2);
-    View gsT = make_view(cur, h0 - 1, w0 - 1, TH + 2, TW + 2);
-    View pz = make_view(cur, hc0 - 3, wc0 - 3, TH / 2 + 6, TW / 2 + 6);
-    View gcA = make_view(cur, hc0 - 3, wc0 - 3, TH / 2 + 6, TW / 2 + 6);
-    View gcB = make_view(cur, hc0 - 3, wc0 - 3, TH / 2 + 6, TW / 2 + 6);
-    View sA1 = make_view(cur, hc0 - 2, wc0 - 2, TH / 2 + 4, TW / 2 + 4);
-    View sB1 = make_view(cur, hc0 - 2, wc0 - 2, TH / 2 + 4, TW / 2 + 4);
-    View gl1 = make_view(cur, hc0 - 2, wc0 - 2, TH / 2 + 4, TW / 2 + 4);
-    View goA1 = make_view(cur, hc0 - 2, wc0 - 2, TH / 2 + 4, TW / 2 + 4);
-    View goB1 = make_view(cur, hc0 - 2, wc0 - 2, TH / 2 + 4, TW / 2 + 4);
-    View lA1 = make_view(cur, hc0 - 1, wc0 - 1, TH / 2 + 2, TW / 2 + 2);
-    View oB1 = make_view(cur, hc0 - 1, wc0 - 1, TH / 2 + 2, TW / 2 + 2);
-    View oT1 = make_view(cur, hc0 - 1, wc0 - 1, TH / 2 + 2, TW / 2 + 2);
-    View gsL1 = make_view(cur, hc0 - 1, wc0 - 1, TH / 2 + 2, TW / 2 + 2);
-    View gsT1 = make_view(cur, hc0 - 1, wc0 - 1, TH / 2 + 2, TW / 2 + 2);
-    View gzc = make_view(cur, hc0, wc0, TH / 2, TW / 2);
-    // the L adjoint reads the neighbours' weights, so wL needs the same (+)2 rectangle as wT here
-    WViews wL0 = make_wviews(cur, h0 - 2, w0 - 2, TH + 4, TW + 4);
-    WViews wT0 = make_wviews(cur, h0 - 2, w0 - 2, TH + 4, TW + 4);
-    WViews wL1 = make_wviews(cur, hc0 - 2, wc0 - 2, TH / 2 + 4, TW / 2 + 4);
-    WViews wT1 = make_wviews(cur, hc0 - 2, wc0 - 2, TH / 2 + 4, TW / 2 + 4);
-    constexpr int NP = BwdSmem<TH, TW>::F0, NPc = BwdSmem<TH, TW>::C0;
-    float* accL0 = cur; cur += 4 * NP;   // edge-weight gradient accumulators, [e][pixel of the tile]
-    float* accT0 = cur; cur += 4 * NP;
-    float* accL1 = cur; cur += 4 * NPc;
-    float* accT1 = cur; cur += 4 * NPc;
-    float* red = cur;
+    auto zf = plane_at<GF, 6>(smem, LY::zf);
+    auto gA = plane_at<GF, 6>(smem, LY::gA);
+    auto gB = plane_at<GF, 6>(smem, LY::gB);
+    auto sA = plane_at<GF, 2>(smem, LY::sA);
+    auto sB = plane_at<GF, 2>(smem, LY::sB);
+    auto gl = plane_at<GF, 2>(smem, LY::gl);
+    auto goA = plane_at<GF, 2>(smem, LY::goA);
+    auto goB = plane_at<GF, 2>(smem, LY::goB);
+    auto lA = plane_at<GF, 1>(smem, LY::lA);
+    auto oB = plane_at<GF, 1>(smem, LY::oB);
+    auto oT = plane_at<GF, 1>(smem, LY::oT);
+    auto gsL = plane_at<GF, 1>(smem, LY::gsL);
+    auto gsT = plane_at<GF, 1>(smem, LY::gsT);
+    auto pz = plane_at<GC, 3>(smem, LY::pz);
+    auto gcA = plane_at<GC, 3>(smem, LY::gcA);
+    auto gcB = plane_at<GC, 3>(smem, LY::gcB);
+    auto sA1 = plane_at<GC, 2>(smem, LY::sA1);
+    auto sB1 = plane_at<GC, 2>(smem, LY::sB1);
+    auto gl1 = plane_at<GC, 2>(smem, LY::gl1);
+    auto goA1 = plane_at<GC, 2>(smem, LY::goA1);
+    auto goB1 = plane_at<GC, 2>(smem, LY::goB1);
+    auto lA1 = plane_at<GC, 1>(smem, LY::lA1);
+    auto oB1 = plane_at<GC, 1>(smem, LY::oB1);
+    auto oT1 = plane_at<GC, 1>(smem, LY::oT1);
+    auto gsL1 = plane_at<GC, 1>(smem, LY::gsL1);
+    auto gsT1 = plane_at<GC, 1>(smem, LY::gsT1);
+    auto wL0 = wplanes_at<GF, 2>(smem, LY::wL0);
+    auto cR0 = plane_at<GF, 2>(smem, LY::cR0);
+    auto cD0 = plane_at<GF, 2>(smem, LY::cD0);
+    auto wT0 = wplanes_at<GF, 2>(smem, LY::wT0);
+    auto wL1 = wplanes_at<GC, 2>(smem, LY::wL1);
+    auto cR1 = plane_at<GC, 2>(smem, LY::cR1);
+    auto cD1 = plane_at<GC, 2>(smem, LY::cD1);
+    auto wT1 = wplanes_at<GC, 2>(smem, LY::wT1);
+    float* red = smem + LY::red;  // [0:16) per-channel stats sums, [16:26) per-graph sums
 
     // ---- per-graph scalars
     const float aT0 = expf(a.p.ro0[g]), aT1 = expf(a.p.ro1[g]);
     const float aL0 = expf(a.p.mu0[g]), aL1 = expf(a.p.mu1[g]);
     const float G0 = expf(a.p.gamma0[g]), G1 = expf(a.p.gamma1[g]);
     const float al0 = a.p.alpha[g], al1 = a.p.alpha[G + g], al2 = a.p.alpha[2 * G + g], be2 = a.p.beta[2 * G + g];
-    const float s0 = a.p.skip ? a.p.skip[0] : 0.f, s1 = a.p.skip ? a.p.skip[1] : 1.f;
+    const bool has_skip = a.p.skip != nullptr;
+    const float s0 = has_skip ? a.p.skip[0] : 0.f, s1 = has_skip ? a.p.skip[1] : 1.f;
     const float c23 = al2 * s1;  // gr2 = c23 * gout
 
-    // ---- weights, accumulators
+    // ---- weights
     const size_t wplane = (size_t)plane * 4;
-    tile_load_weights(wT0, a.wT0 + wplane * HW, H, W);
-    tile_load_weights(wT1, a.wT1 + wplane * HWc, Hc, Wc);
-    if (HAS_A) {
-        tile_load_weights(wL0, a.wL0 + wplane * HW, H, W);
-        tile_load_weights(wL1, a.wL1 + wplane * HWc, Hc, Wc);
+    if (THR) {
+        load_weights(gf, wT0, a.wT0 + wplane * HW);
+        load_weights(gc, wT1, a.wT1 + wplane * HWc);
+    } else {
+        load_gtv_coeffs(gf, cR0, cD0, a.wT0 + wplane * HW);
+        load_gtv_coeffs(gc, cR1, cD1, a.wT1 + wplane * HWc);
     }
-    TILE_LOOP(i, 8 * NP + 8 * NPc) accL0[i] = 0.f;
+    if (HAS_A) {
+        load_weights(gf, wL0, a.wL0 + wplane * HW);
+        load_weights(gc, wL1, a.wL1 + wplane * HWc);
+    }
+    TILE_LOOP(i, 32) red[i] = 0.f;
 
-    // per-graph sums: 0 mu0, 1 ro0, 2 mu1, 3 ro1, 4 gamma0, 5 gamma1, 6 alpha_k, 7 beta2, 8 skip0, 9 skip1
-    float gsum[10];
+    // edge-weight gradient accumulators of this thread's epilogue quad: [L e][4] + [T e][4]
+    ACC_DECL(accF, NQF, 32);
+    ACC_DECL(accC, NQC, 32);
+#ifdef GLRGTV_EMU
+    for (int i = 0; i < NQF * 32; ++i) accF_store[i] = 0.f;
+    for (int i = 0; i < NQC * 32; ++i) accC_store[i] = 0.f;
+#else
+    float acc_regs[32];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) gsum[k] = 0.f;
+    for (int i = 0; i < 32; ++i) acc_regs[i] = 0.f;
+#endif
+    // per-graph sums of this thread: fine [mu0, ro0, gamma0, alpha_k, beta2, skip0, skip1], coarse [mu1, ro1, gamma1]
+    float gsF[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gsC[3] = {0.f, 0.f, 0.f};
 
     for (int f = 0; f < F; ++f) {
         const int c = g * F + f;
         const size_t off = ((size_t)b * G * F + c) * HW;
         const StatsTaps kT0 = glr_load_taps(a.p.gtv0.stats, c), kT1 = glr_load_taps(a.p.gtv1.stats, c);
         const StatsTaps kL0 = glr_load_taps(a.p.glr0.stats, c), kL1 = glr_load_taps(a.p.glr1.stats, c);
-        // per-channel stats sums: [module T0,L0,T1,L1][p01,p02a,p02b,p03]
-        float st[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) st[k] = 0.f;
-        float(&stT0)[4] = *reinterpret_cast<float(*)[4]>(st + 0);
-        float(&stL0)[4] = *reinterpret_cast<float(*)[4]>(st + 4);
-        float(&stT1)[4] = *reinterpret_cast<float(*)[4]>(st + 8);
-        float(&stL1)[4] = *reinterpret_cast<float(*)[4]>(st + 12);
 
         __syncthreads();
-        // ---- phase 1: stage input (clamp-extended) and upstream gradients (zero-extended)
-        tile_load_clamped(zf, a.z + off, H, W);
-        TILE_LOOP(i, gA.size()) {
-            int h = gA.oh + i / gA.nw, w = gA.ow + i % gA.nw;
-            float va = 0.f, vb = 0.f;
-            if (glr_inside(h, w, H, W)) {
-                const size_t gi = off + (size_t)h * W + w;
-                if (MODE == BWD_X3) {
-                    va = -c23 * a.gout[gi];
-                } else if (MODE == BWD_X2) {
-                    float gr2 = c23 * a.gout[gi];
-                    float gr1 = be2 * gr2 + al1 * a.gin[gi];
-                    va = -gr1;
-                    vb = gr2 + gr1;
-                } else if (MODE == BWD_X1) {
-                    va = -al0 * a.gin[gi];
-                } else {
-                    vb = a.gin[gi];
-                }
-            }
-            if (HAS_A) gA.p[i] = va;
-            if (HAS_R) gB.p[i] = vb;
-        }
-        __syncthreads();
-        // ---- phase 2: forward S + pooling; adjoint of St on the upstreams; pooled upstreams
-        if (HAS_A) tile_S2(sA, kL0, sB, kT0, zf, H, W);
-        else tile_S(sB, zf, kT0, H, W);
-        tile_pool(pz, zf, Hc, Wc);
-        if (HAS_A) {
-            tile_Szero<false>(gl, gA, kL0, aL0, H, W);
-            tile_Szero<true>(goA, gA, kT0, aT0, H, W);
-        }
-        if (HAS_R) tile_Szero<true>(goB, gB, kT0, aT0, H, W);
-        TILE_LOOP(i, gcA.size()) {  // VJP of P^T is P: mean of the 2x2 block, zero outside the coarse image
-            int h = gcA.oh + i / gcA.nw, w = gcA.ow + i % gcA.nw;
-            float va = 0.f, vb = 0.f;
-            if (glr_inside(h, w, Hc, Wc)) {
-                if (HAS_A) { const float* q = &gA.at(2 * h, 2 * w); va = 0.25f * (q[0] + q[1] + q[gA.nw] + q[gA.nw + 1]); }
-                if (HAS_R) { const float* q = &gB.at(2 * h, 2 * w); vb = 0.25f * (q[0] + q[1] + q[gB.nw] + q[gB.nw + 1]); }
-            }
-            if (HAS_A) gcA.p[i] = va;
-            if (HAS_R) gcB.p[i] = vb;
-        }
-        __syncthreads();
-        // ---- phase 3: forward cores (fine), coarse S; adjoint cores (fine), coarse St-adjoints
-        if (HAS_A) tile_L(lA, sA, wL0, H, W);
-        tile_gtv_core<false>(oB, sB, wT0, 0.f, H, W);
-        if (THR) tile_gtv_core<true>(oT, sB, wT0, G0, H, W);
-        if (HAS_A) tile_S2(sA1, kL1, sB1, kT1, pz, Hc, Wc);
-        else tile_S(sB1, pz, kT1, Hc, Wc);
-        if (HAS_A) {
-            tile_L_adj(gsL, gl, wL0, H, W);
-            tile_gtv_core<false>(gsT, goA, wT0, 0.f, H, W);  // the linear core is self-adjoint
-            if (THR) tile_gtv_core_thr_adj<true>(gsT, goB, sB, wT0, G0, H, W);
-            tile_Szero<false>(gl1, gcA, kL1, aL1, Hc, Wc);
-            tile_Szero<true>(goA1, gcA, kT1, aT1, Hc, Wc);
-        } else {
-            tile_gtv_core<false>(gsT, goB, wT0, 0.f, H, W);
-        }
-        if (HAS_R) tile_Szero<true>(goB1, gcB, kT1, aT1, Hc, Wc);
-        __syncthreads();
-        // ---- phase 4: coarse cores, forward and adjoint
-        if (HAS_A) tile_L(lA1, sA1, wL1, Hc, Wc);
-        tile_gtv_core<false>(oB1, sB1, wT1, 0.f, Hc, Wc);
-        if (THR) tile_gtv_core<true>(oT1, sB1, wT1, G1, Hc, Wc);
-        if (HAS_A) {
-            tile_L_adj(gsL1, gl1, wL1, Hc, Wc);
-            tile_gtv_core<false>(gsT1, goA1, wT1, 0.f, Hc, Wc);
-            if (THR) tile_gtv_core_thr_adj<true>(gsT1, goB1, sB1, wT1, G1, Hc, Wc);
-        } else {
-            tile_gtv_core<false>(gsT1, goB1, wT1, 0.f, Hc, Wc);
-        }
-        __syncthreads();
-        // ---- phase 5: coarse epilogue: gradient wrt P z, parameter sums, coarse edge-weight gradients
-        TILE_LOOP(i, gzc.size()) {
-            const int lh = i / gzc.nw, lw = i % gzc.nw, h = hc0 + lh, w = wc0 + lw;
-            if (h >= Hc || w >= Wc) { gzc.p[i] = 0.f; continue; }
-            float v = tile_S_adj_at(gsT1, kT1, h, w, Hc, Wc);
-            if (HAS_A) v += tile_S_adj_at(gsL1, kL1, h, w, Hc, Wc);
-            gzc.p[i] = v;
-            const float ga = HAS_A ? gcA.at(h, w) : 0.f, gb = HAS_R ? gcB.at(h, w) : 0.f;
-            // forward values for the mu1 / ro1 gradients
-            const float gtv_lin = tile_St_at(oB1, kT1, h, w);
-            if (HAS_A) {
-                gsum[2] += aL1 * ga * tile_St_at(lA1, kL1, h, w);
-                gsum[3] += aT1 * ga * gtv_lin;
-                stats_acc_St(stL1, aL1 * ga, lA1, h, w);
-                stats_acc_S(stL1, gsL1.at(h, w), pz, h, w);
-                stats_acc_St(stT1, aT1 * ga, oB1, h, w);
-            }
-            if (HAS_R) {
-                gsum[3] += aT1 * gb * (THR ? tile_St_at(oT1, kT1, h, w) : gtv_lin);
-                stats_acc_St(stT1, aT1 * gb, THR ? oT1 : oB1, h, w);
-            }
-            stats_acc_S(stT1, gsT1.at(h, w), pz, h, w);
-            // edge weights
-            const int pi = lh * (TW / 2) + lw;
-            if (HAS_A) {
-                const float glv = gl1.at(h, w);
-                const float* cs = &sA1.at(h, w);
-                accL1[0 * NPc + pi] -= glv * cs[-sA1.nw];
-                accL1[1 * NPc + pi] -= glv * cs[-1];
-                accL1[2 * NPc + pi] -= glv * cs[1];
-                accL1[3 * NPc + pi] -= glv * cs[sA1.nw];
-                gtv_edge_grads<false>(accT1 + pi, NPc, goA1, sB1, wT1, 0.f, h, w);
-            }
-            if (HAS_R) {
-                if (THR) gsum[5] += gtv_edge_grads<true>(accT1 + pi, NPc, goB1, sB1, wT1, G1, h, w);
-                else gtv_edge_grads<false>(accT1 + pi, NPc, goB1, sB1, wT1, 0.f, h, w);
-            }
-        }
-        __syncthreads();
-        // ---- phase 6: fine epilogue
-        TILE_LOOP(i, TH * TW) {
-            const int lh = i / TW, lw = i % TW, h = h0 + lh, w = w0 + lw;
-            if (h >= H || w >= W) continue;
+        // ---- phase 0: stage input (clamp-extended) and upstream gradients (zero-extended)
+        load_plane<true>(gf, zf, a.z + off);
+        TILE_LOOP(i, GF::items(6)) {
+            QUAD_ITEM(GF, 6, i, r, cq);
+            const int h = gf.gh(r, 6), w = gf.gw(cq);
+            float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+            float q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f};
             const size_t gi = off + (size_t)h * W + w;
-            const float zv = zf.at(h, w);
-            const float ga = HAS_A ? gA.at(h, w) : 0.f, gb = HAS_R ? gB.at(h, w) : 0.f;
-            float V = ga + tile_S_adj_at(gsT, kT0, h, w, H, W) + 0.25f * gzc.at(h >> 1, w >> 1);
-            if (HAS_A) V += tile_S_adj_at(gsL, kL0, h, w, H, W);
-            // forward values
-            const float gtv_lin = tile_St_at(oB, kT0, h, w);
-            float glr = 0.f;
-            if (HAS_A) {
-                glr = tile_St_at(lA, kL0, h, w);
-                gsum[0] += aL0 * ga * glr;
-                gsum[1] += aT0 * ga * gtv_lin;
-                stats_acc_St(stL0, aL0 * ga, lA, h, w);
-                stats_acc_S(stL0, gsL.at(h, w), zf, h, w);
-                stats_acc_St(stT0, aT0 * ga, oB, h, w);
-            }
-            if (HAS_R) {
-                gsum[1] += aT0 * gb * (THR ? tile_St_at(oT, kT0, h, w) : gtv_lin);
-                stats_acc_St(stT0, aT0 * gb, THR ? oT : oB, h, w);
-            }
-            stats_acc_S(stT0, gsT.at(h, w), zf, h, w);
-            // edge weights
-            const int pi = lh * TW + lw;
-            if (HAS_A) {
-                const float glv = gl.at(h, w);
-                const float* cs = &sA.at(h, w);
-                accL0[0 * NP + pi] -= glv * cs[-sA.nw];
-                accL0[1 * NP + pi] -= glv * cs[-1];
-                accL0[2 * NP + pi] -= glv * cs[1];
-                accL0[3 * NP + pi] -= glv * cs[sA.nw];
-                gtv_edge_grads<false>(accT0 + pi, NP, goA, sB, wT0, 0.f, h, w);
-            }
-            if (HAS_R) {
-                if (THR) gsum[4] += gtv_edge_grads<true>(accT0 + pi, NP, goB, sB, wT0, G0, h, w);
-                else gtv_edge_grads<false>(accT0 + pi, NP, goB, sB, wT0, 0.f, h, w);
-            }
-            // stage epilogue
-            (void)zv;
-            float outv;
-            if (MODE == BWD_X3) {
-                const float go_ = a.gout[gi];
-                outv = s1 * go_ + V;
-            } else if (MODE == BWD_X2) {
-                const float gx2v = a.gin[gi];
-                outv = gx2v + V;
-                gsum[6] += gx2v * a.r1[gi];
-            } else if (MODE == BWD_X1) {
-                outv = (1.f + al0) * a.gin[gi] + V;
+            constexpr bool need0 = MODE == BWD_X3 || MODE == BWD_X2, need1 = MODE != BWD_X3;   // gout / gin
+            if (vec && gf.quad_inside(h, w)) {
+                if (need0) ld4(a.gout + gi, q0);
+                if (need1) ld4(a.gin + gi, q1);
             } else {
-                const float go_ = a.gout[gi];
-                const float gr2 = c23 * go_;
-                const float gbB = gr2 + be2 * gr2 + al1 * a.gx2[gi];
-                outv = a.gin[gi] + V + gbB + s0 * go_;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (gf.inside(h, w + j)) {
+                        if (need0) q0[j] = a.gout[gi + j];
+                        if (need1) q1[j] = a.gin[gi + j];
+                    }
             }
-            a.gz_out[gi] = outv;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (MODE == BWD_X3) va[j] = -c23 * q0[j];
+                else if (MODE == BWD_X2) {
+                    const float gr2 = c23 * q0[j], gr1 = be2 * gr2 + al1 * q1[j];
+                    va[j] = -gr1;
+                    vb[j] = gr2 + gr1;
+                } else if (MODE == BWD_X1) va[j] = -al0 * q1[j];
+                else vb[j] = q1[j];
+            }
+            if (HAS_A) st4(gA.lrc(r, cq), va);
+            if (HAS_R) st4(gB.lrc(r, cq), vb);
         }
-        // X3 / X1 also need A(z) itself (r2, u2, x3 / bA - A bA): a second pass once the coarse forward term is known
-        if (MODE == BWD_X3 || MODE == BWD_X1) {
-            TILE_LOOP(i, TH * TW) {
-                const int h = h0 + i / TW, w = w0 + i % TW;
-                if (h >= H || w >= W) continue;
-                const size_t gi = off + (size_t)h * W + w;
-                const float zv = zf.at(h, w);
-                const int hc = h >> 1, wc = w >> 1;
-                const float tcv = aL1 * tile_St_at(lA1, kL1, hc, wc) + aT1 * tile_St_at(oB1, kT1, hc, wc);
-                const float Az = zv + aL0 * tile_St_at(lA, kL0, h, w) + aT0 * tile_St_at(oB, kT0, h, w) + 0.25f * tcv;
+        __syncthreads();
+        // ---- phase 1: forward S + pooling; adjoint of St on the upstreams; pooled upstreams
+        stage_S<HAS_A>(gf, HAS_A ? sA : sB, HAS_A ? kL0 : kT0, sB, kT0, zf);
+        stage_pool(gc, pz, zf);
+        if (HAS_A) {
+            stage_Szero<false>(gf, gl, gA, kL0, aL0);
+            stage_Szero<true>(gf, goA, gA, kT0, aT0);
+            stage_pool_zero(gc, gcA, gA);
+        }
+        if (HAS_R) {
+            stage_Szero<true>(gf, goB, gB, kT0, aT0);
+            stage_pool_zero(gc, gcB, gB);
+        }
+        __syncthreads();
+        // ---- phase 2: forward cores (fine), coarse S; adjoint cores (fine), coarse St-adjoints
+        if (HAS_A) stage_L(gf, lA, sA, wL0);
+        if (THR) {
+            stage_gtv_lin_raw(gf, oB, sB, wT0);
+            stage_gtv_thr(gf, oT, sB, wT0, G0);
+        } else {
+            stage_gtv_lin(gf, oB, sB, cR0, cD0);
+        }
+        stage_S<HAS_A>(gc, HAS_A ? sA1 : sB1, HAS_A ? kL1 : kT1, sB1, kT1, pz);
+        if (HAS_A) {
+            stage_L_adj(gf, gsL, gl, wL0);
+            if (THR) stage_gtv_lin_raw(gf, gsT, goA, wT0);   // the linear core is self-adjoint
+            else stage_gtv_lin(gf, gsT, goA, cR0, cD0);
+            stage_Szero<false>(gc, gl1, gcA, kL1, aL1);
+            stage_Szero<true>(gc, goA1, gcA, kT1, aT1);
+        } else {
+            stage_gtv_lin(gf, gsT, goB, cR0, cD0);
+        }
+        if (HAS_R) stage_Szero<true>(gc, goB1, gcB, kT1, aT1);
+        __syncthreads();
+        // ---- phase 3: the thresholded adjoint adds into gsT; coarse cores, forward and adjoint
+        if (THR) stage_gtv_thr_adj_add(gf, gsT, goB, sB, wT0, G0);
+        if (HAS_A) stage_L(gc, lA1, sA1, wL1);
+        if (THR) {
+            stage_gtv_lin_raw(gc, oB1, sB1, wT1);
+            stage_gtv_thr(gc, oT1, sB1, wT1, G1);
+        } else {
+            stage_gtv_lin(gc, oB1, sB1, cR1, cD1);
+        }
+        if (HAS_A) {
+            stage_L_adj(gc, gsL1, gl1, wL1);
+            if (THR) stage_gtv_lin_raw(gc, gsT1, goA1, wT1);
+            else stage_gtv_lin(gc, gsT1, goA1, cR1, cD1);
+        } else {
+            stage_gtv_lin(gc, gsT1, goB1, cR1, cD1);
+        }
+        __syncthreads();
+        if (THR) {   // (needs the linear part of gsT1 complete)
+            stage_gtv_thr_adj_add(gc, gsT1, goB1, sB1, wT1, G1);
+            __syncthreads();
+        }
+        // ---- phase 4: epilogues.  Threads [0, NQF) own one fine quad each, threads [NQF, NQF+NQC) one coarse quad.
+        float stF[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, stC[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        EPI_LOOP(i, NQC, NQF) {
+            QUAD_ITEM(GC, 0, i, r, cq);
+            const int h = gc.h0 + r, w = gc.gw(cq);
+            if (h >= gc.H || w >= gc.W) continue;
+            QuadWork<MODE, GC, 3> qw{gc, pz, sA1, sB1, gl1, goA1, goB1, lA1, oB1, oT1, gsL1, gsT1,
+                                     a.wT1 + wplane * HWc, kT1, kL1, aT1, aL1, G1};
+            float ga[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f}, V[4], glr[4], gtvl[4];
+            if (HAS_A) ld4(gcA.lrc(r + 3, cq), ga);
+            if (HAS_R) ld4(gcB.lrc(r + 3, cq), gb);
+            qw.run(r, cq, ga, gb, stC, gsC, ACC_PTR(accC, i, 32), V, glr, gtvl);
+        }
+        EPI_LOOP(i, NQF, 0) {
+            QUAD_ITEM(GF, 0, i, r, cq);
+            const int h = gf.h0 + r, w = gf.gw(cq);
+            if (h >= H || w >= W) continue;
+            QuadWork<MODE, GF, 6> qw{gf, zf, sA, sB, gl, goA, goB, lA, oB, oT, gsL, gsT,
+                                     a.wT0 + wplane * HW, kT0, kL0, aT0, aL0, G0};
+            float ga[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f}, V[4], glr[4], gtvl[4];
+            if (HAS_A) ld4(gA.lrc(r + 6, cq), ga);
+            if (HAS_R) ld4(gB.lrc(r + 6, cq), gb);
+            qw.run(r, cq, ga, gb, stF, gsF, ACC_PTR(accF, i, 32), V, glr, gtvl);
+            // gradient coming back through the coarse branch (VJP of P is P^T: 0.25 * replicate), inline per coarse pixel
+            const int rc = (r >> 1) + 1, cc = (cq >> 1) + 4, hc = h >> 1, wc = (w >> 1);
+            float gz0 = S_adj_elem(gsT1.lrc(rc, cc), GC::P, kT1, hc, wc, gc.H, gc.W);
+            float gz1 = S_adj_elem(gsT1.lrc(rc, cc + 1), GC::P, kT1, hc, wc + 1, gc.H, gc.W);
+            if (HAS_A) {
+                gz0 += S_adj_elem(gsL1.lrc(rc, cc), GC::P, kL1, hc, wc, gc.H, gc.W);
+                gz1 += S_adj_elem(gsL1.lrc(rc, cc + 1), GC::P, kL1, hc, wc + 1, gc.H, gc.W);
+            }
+            float zq[4];
+            ld4(zf.lrc(r + 6, cq), zq);
+            // forward A(z) where the stage needs it (coarse forward term inline, as in the forward kernel)
+            float Az[4] = {0.f, 0.f, 0.f, 0.f};
+            if (MODE == BWD_X3 || MODE == BWD_X1) {
+                const float t0 = aT1 * St_elem(oB1.lrc(rc, cc), GC::P, kT1) + aL1 * St_elem(lA1.lrc(rc, cc), GC::P, kL1);
+                const float t1 = aT1 * St_elem(oB1.lrc(rc, cc + 1), GC::P, kT1) + aL1 * St_elem(lA1.lrc(rc, cc + 1), GC::P, kL1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) Az[j] = zq[j] + aL0 * glr[j] + aT0 * gtvl[j] + 0.25f * (j < 2 ? t0 : t1);
+            }
+            const size_t gi = off + (size_t)h * W + w;
+            const bool full = vec && w + 3 < W;
+            float q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f}, q2[4] = {0.f, 0.f, 0.f, 0.f},
+                  q3[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f}, outv[4];
+            // pointwise operands: q0 gout, q1 gin, q2 r1 / gx2, q3 bB, q4 x
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = full || w + j < W;
+                if (!ok) continue;
+                if (MODE == BWD_X3 || MODE == BWD_X2 || MODE == BWD_BA) q0[j] = a.gout[gi + j];
+                if (MODE != BWD_X3) q1[j] = a.gin[gi + j];
+                if (MODE == BWD_X3 || MODE == BWD_X2) q2[j] = a.r1[gi + j];
+                if (MODE == BWD_BA) q2[j] = a.gx2[gi + j];
+                if (MODE == BWD_X3) { q3[j] = a.bB[gi + j]; if (has_skip) q4[j] = a.x[gi + j]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float Vj = (HAS_A ? ga[j] : 0.f) + V[j] + 0.25f * (j < 2 ? gz0 : gz1);
                 if (MODE == BWD_X3) {
-                    const float r1v = a.r1[gi], go_ = a.gout[gi];
-                    const float u2 = (a.bB[gi] - Az) + be2 * r1v;
-                    const float x3 = zv + al2 * u2;
-                    const float g3 = s1 * go_;
-                    gsum[6] += g3 * u2;
-                    gsum[7] += al2 * g3 * r1v;
-                    if (a.p.skip) { gsum[8] += go_ * a.x[gi]; gsum[9] += go_ * x3; }
+                    const float u2 = (q3[j] - Az[j]) + be2 * q2[j], x3 = zq[j] + al2 * u2, g3 = s1 * q0[j];
+                    outv[j] = g3 + Vj;
+                    gsF[3] += g3 * u2;
+                    gsF[4] += al2 * g3 * q2[j];
+                    if (has_skip) { gsF[5] += q0[j] * q4[j]; gsF[6] += q0[j] * x3; }
+                } else if (MODE == BWD_X2) {
+                    outv[j] = q1[j] + Vj;
+                    gsF[3] += q1[j] * q2[j];
+                } else if (MODE == BWD_X1) {
+                    outv[j] = (1.f + al0) * q1[j] + Vj;
+                    gsF[3] += q1[j] * (zq[j] - Az[j]);
                 } else {
-                    gsum[6] += a.gin[gi] * (zv - Az);
+                    const float gr2 = c23 * q0[j];
+                    outv[j] = q1[j] + Vj + (gr2 + be2 * gr2 + al1 * q2[j]) + s0 * q0[j];
                 }
             }
+            if (full) st4(a.gz_out + gi, outv);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (w + j < W) a.gz_out[gi + j] = outv[j];
+            }
         }
-        // ---- per-channel stats gradients
-        block_sum_n<16>(st, red);
-        if (threadIdx.x == 0) {
-            const int C = G * F;
+        // ---- per-channel stats gradients: warp shuffles -> shared atomics -> one global atomic per value
+        warp_commit<8>(stF, red);
+        warp_commit<8>(stC, red + 8);
+        __syncthreads();
+        {
             float* dst[4] = {a.gr.gtv0_stats, a.gr.glr0_stats, a.gr.gtv1_stats, a.gr.glr1_stats};
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                if (!HAS_A && (m == 1 || m == 3)) continue;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) atomicAdd(&dst[m][k * C + c], st[m * 4 + k]);
+            const int C = G * F;
+            TILE_LOOP(t, 16) {   // red: fine [T0 | L0], coarse [T1 | L1], 4 values each
+                const int m = ((t >> 3) << 1) | ((t >> 2) & 1), k = t & 3;
+                if (HAS_A || m == 0 || m == 2) atomicAdd(&dst[m][k * C + c], red[t]);
+                red[t] = 0.f;
             }
         }
     }
 
     // ---- edge-weight gradients of this tile: one read-modify-write per stage
-    __syncthreads();
     {
-        float* gw0[2] = {a.gwT0 + wplane * HW, a.gwL0 + wplane * HW};
-        const float* acc0[2] = {accT0, accL0};
-        for (int m = 0; m < (HAS_A ? 2 : 1); ++m)
-            TILE_LOOP(i, 4 * TH * TW) {
-                const int e = i / (TH * TW), pi = i % (TH * TW), h = h0 + pi / TW, w = w0 + pi % TW;
-                if (h >= H || w >= W) continue;
-                float* q = gw0[m] + (size_t)e * HW + (size_t)h * W + w;
-                const float v = acc0[m][e * NP + pi];
-                *q = a.gw_assign ? v : *q + v;
+        float* gwF[2] = {a.gwL0 + wplane * HW, a.gwT0 + wplane * HW};
+        EPI_LOOP(i, NQF, 0) {
+            QUAD_ITEM(GF, 0, i, r, cq);
+            const int h = gf.h0 + r, w = gf.gw(cq);
+            if (h >= H || w >= W) continue;
+            const float* acc = ACC_PTR(accF, i, 32);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (!HAS_A && m == 0) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float* q = gwF[m] + (size_t)e * HW + (size_t)h * W + w;
+                    float v[4] = {acc[m * 16 + e * 4 + 0], acc[m * 16 + e * 4 + 1], acc[m * 16 + e * 4 + 2], acc[m * 16 + e * 4 + 3]};
+                    if (vec && w + 3 < W) {
+                        if (!a.gw_assign) { float o[4]; ld4(q, o); v[0] += o[0]; v[1] += o[1]; v[2] += o[2]; v[3] += o[3]; }
+                        st4(q, v);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (w + j < W) q[j] = a.gw_assign ? v[j] : q[j] + v[j];
+                    }
+                }
             }
-        float* gw1[2] = {a.gwT1 + wplane * HWc, a.gwL1 + wplane * HWc};
-        const float* acc1[2] = {accT1, accL1};
-        for (int m = 0; m < (HAS_A ? 2 : 1); ++m)
-            TILE_LOOP(i, TH * TW) {  // 4 * (TH/2) * (TW/2)
-                const int e = i / (TH * TW / 4), pi = i % (TH * TW / 4), h = hc0 + pi / (TW / 2), w = wc0 + pi % (TW / 2);
-                if (h >= Hc || w >= Wc) continue;
-                float* q = gw1[m] + (size_t)e * HWc + (size_t)h * Wc + w;
-                const float v = acc1[m][e * NPc + pi];
-                *q = a.gw_assign ? v : *q + v;
+        }
+        float* gwC[2] = {a.gwL1 + wplane * HWc, a.gwT1 + wplane * HWc};
+        EPI_LOOP(i, NQC, NQF) {
+            QUAD_ITEM(GC, 0, i, r, cq);
+            const int h = gc.h0 + r, w = gc.gw(cq);
+            if (h >= gc.H || w >= gc.W) continue;
+            const float* acc = ACC_PTR(accC, i, 32);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (!HAS_A && m == 0) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float* q = gwC[m] + (size_t)e * HWc + (size_t)h * gc.W + w;
+                    float v[4] = {acc[m * 16 + e * 4 + 0], acc[m * 16 + e * 4 + 1], acc[m * 16 + e * 4 + 2], acc[m * 16 + e * 4 + 3]};
+                    if (vecc && w + 3 < gc.W) {
+                        if (!a.gw_assign) { float o[4]; ld4(q, o); v[0] += o[0]; v[1] += o[1]; v[2] += o[2]; v[3] += o[3]; }
+                        st4(q, v);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (w + j < gc.W) q[j] = a.gw_assign ? v[j] : q[j] + v[j];
+                    }
+                }
             }
+        }
     }
     // ---- per-graph scalar gradients
-    block_sum_n<10>(gsum, red);
+    __syncthreads();
+    warp_commit<7>(gsF, red + 16);
+    warp_commit<3>(gsC, red + 23);
+    __syncthreads();
     if (threadIdx.x == 0) {
+        const float* s = red + 16;  // mu0, ro0, gamma0, alpha_k, beta2, skip0, skip1, mu1, ro1, gamma1
         if (HAS_A) {
-            atomicAdd(&a.gr.mu0[g], gsum[0]);
-            atomicAdd(&a.gr.mu1[g], gsum[2]);
+            atomicAdd(&a.gr.mu0[g], s[0]);
+            atomicAdd(&a.gr.mu1[g], s[7]);
         }
-        atomicAdd(&a.gr.ro0[g], gsum[1]);
-        atomicAdd(&a.gr.ro1[g], gsum[3]);
+        atomicAdd(&a.gr.ro0[g], s[1]);
+        atomicAdd(&a.gr.ro1[g], s[8]);
         if (THR) {
-            atomicAdd(&a.gr.gamma0[g], gsum[4] * G0);
-            atomicAdd(&a.gr.gamma1[g], gsum[5] * G1);
+            atomicAdd(&a.gr.gamma0[g], s[2] * G0);
+            atomicAdd(&a.gr.gamma1[g], s[9] * G1);
         }
         if (MODE == BWD_X3) {
-            atomicAdd(&a.gr.alpha[2 * G + g], gsum[6]);
-            atomicAdd(&a.gr.beta[2 * G + g], gsum[7]);
-            if (a.p.skip && a.gr.skip) {
-                atomicAdd(&a.gr.skip[0], gsum[8]);
-                atomicAdd(&a.gr.skip[1], gsum[9]);
+            atomicAdd(&a.gr.alpha[2 * G + g], s[3]);
+            atomicAdd(&a.gr.beta[2 * G + g], s[4]);
+            if (has_skip && a.gr.skip) {
+                atomicAdd(&a.gr.skip[0], s[5]);
+                atomicAdd(&a.gr.skip[1], s[6]);
             }
         }
-        if (MODE == BWD_X2) atomicAdd(&a.gr.alpha[G + g], gsum[6]);
-        if (MODE == BWD_X1) atomicAdd(&a.gr.alpha[g], gsum[6]);
+        if (MODE == BWD_X2) atomicAdd(&a.gr.alpha[G + g], s[3]);
+        if (MODE == BWD_X1) atomicAdd(&a.gr.alpha[g], s[3]);
     }
 }
 
@@ -452,7 +640,7 @@ __global__ void __launch_bounds__(512) k_block_bwd_stage(BlockBwdArgs a) {
 #define GLR_BTH 32
 #define GLR_BTW 32
 #endif
-#define GLR_BWD_THREADS 512
+#define GLR_BWD_THREADS 384
 
 template <int MODE>
 static int launch_bwd_stage(const BlockBwdArgs& a, void* stream) {
@@ -460,19 +648,20 @@ static int launch_bwd_stage(const BlockBwdArgs& a, void* stream) {
     const long tiles = (long)((s.W + GLR_BTW - 1) / GLR_BTW) * ((s.H + GLR_BTH - 1) / GLR_BTH);
     const long blocks = tiles * s.B * s.G;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
-    constexpr size_t smem = BwdSmem<GLR_BTH, GLR_BTW>::value * sizeof(float);
+    constexpr size_t smem = (size_t)BwdLayout<MODE, GLR_BTH, GLR_BTW>::total * sizeof(float);
     static_assert(smem <= 227 * 1024, "backward tile does not fit shared memory");
 #ifndef GLRGTV_EMU
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return glr_record_launch_error();
         configured = true;
     }
 #endif
     GLR_PROF_BEGIN(GLRGTV_SLOT_BWD_X3 + MODE, stream);
-    GLR_LAUNCH((k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW>), dim3((unsigned)blocks), GLR_BWD_THREADS, smem, stream, a);
+    GLR_LAUNCH((k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS>), dim3((unsigned)blocks), GLR_BWD_THREADS, smem,
+               stream, a);
     GLR_PROF_END(GLRGTV_SLOT_BWD_X3 + MODE, stream);
     return GLR_CHECK_LAUNCH();
 }
@@ -482,14 +671,16 @@ int glr_edge_weights_bwd_strided(const glrgtv_shape* s, const glrgtv_window* win
                                  const float* multiM, const float* w, const float* gw, float* gfeat, size_t gfeat_bs,
                                  float* gmultiM, float* scratch, void* stream);
 
+// workspace layout in floats; every segment starts 16-byte aligned
 static size_t ws_floats(const glrgtv_shape* s, size_t* o_gx2, size_t* o_gx1, size_t* o_gbA, size_t* o_gw, size_t* o_scr) {
     const size_t N = (size_t)s->B * s->H * s->W, C = (size_t)s->G * s->F, GE = (size_t)s->G * 4;
+    auto up = [](size_t v) { return (v + 3) & ~(size_t)3; };
     size_t off = 0;
-    *o_gx2 = off; off += C * N;
-    *o_gx1 = off; off += C * N;
-    *o_gbA = off; off += C * N;
-    *o_gw = off;  off += 2 * GE * N + 2 * GE * (N / 4);
-    *o_scr = off; off += (size_t)s->G * 5 * N;
+    *o_gx2 = off; off = up(off + C * N);
+    *o_gx1 = off; off = up(off + C * N);
+    *o_gbA = off; off = up(off + C * N);
+    *o_gw = off;  off = up(off + 2 * GE * N + 2 * GE * (N / 4));
+    *o_scr = off; off = up(off + (size_t)s->G * 5 * N);
     return off;
 }
 
@@ -512,7 +703,11 @@ extern "C" int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params
     GLR_REQUIRE_PTR(gx); GLR_REQUIRE_PTR(gfeat0); GLR_REQUIRE_PTR(gfeat1); GLR_REQUIRE_PTR(workspace);
     if (!sv || !gr) return GLRGTV_ERR_POINTER;
     const float* need[9] = {sv->wT0, sv->wL0, sv->wT1, sv->wL1, sv->bA, sv->x1, sv->bB, sv->r1, sv->x2};
-    for (int i = 0; i < 9; ++i) GLR_REQUIRE_PTR(need[i]);
+    for (int i = 0; i < 9; ++i) {
+        GLR_REQUIRE_PTR(need[i]);
+        if (!glr_aligned16(need[i])) return GLRGTV_ERR_POINTER;
+    }
+    if (!glr_aligned16(x) || !glr_aligned16(gout) || !glr_aligned16(gx) || !glr_aligned16(workspace)) return GLRGTV_ERR_POINTER;
     float* const* gp = &gr->gtv0_stats;
     for (int i = 0; i < 16; ++i) GLR_REQUIRE_PTR(gp[i]);
     if (p->skip) GLR_REQUIRE_PTR(gr->skip);

@@ -13,7 +13,7 @@
 //
 // with R(z) = e^ro0 St0 Ct0 phi(C0 S0 z) + P^T e^ro1 St1 Ct1 phi(C1 S1 P z), phi = identity (R_lin) or
 // 2*soft-threshold - id (bB).  Tile = TH x TW fine pixels, input halo 6 (3 for the fine chain, 3 coarse
-// pixels = 6 fine for the half-resolution chain).
+// pixels = 6 fine for the half-resolution chain).  Stage arithmetic lives in tile.cuh.
 #include "tile.cuh"
 
 enum { MODE_BA = 0, MODE_X1 = 1, MODE_X2 = 2, MODE_X3 = 3 };
@@ -31,50 +31,70 @@ struct BlockFwdArgs {
     float* out2;  // X2: r1
 };
 
-template <int TH, int TW>
-struct FwdSmem {
-    // number of floats the kernel carves (upper bound over modes), each view rounded up to 4 floats
-    static constexpr int r4(int n) { return (n + 3) & ~3; }
-    static constexpr int value =
-        r4((TH + 12) * (TW + 12)) + 2 * r4((TH + 4) * (TW + 4)) + 3 * r4((TH + 2) * (TW + 2)) +
-        r4((TH / 2 + 6) * (TW / 2 + 6)) + 2 * r4((TH / 2 + 4) * (TW / 2 + 4)) + 3 * r4((TH / 2 + 2) * (TW / 2 + 2)) +
-        2 * r4((TH / 2) * (TW / 2)) + 4 * r4((TH + 2) * (TW + 2)) + 4 * r4((TH + 4) * (TW + 4)) +
-        4 * r4((TH / 2 + 2) * (TW / 2 + 2)) + 4 * r4((TH / 2 + 4) * (TW / 2 + 4)) + 32;
+// shared-memory layout (floats) of one forward stage
+template <int MODE, int TH, int TW>
+struct FwdLayout {
+    using GF = Geo<TH, TW>;
+    using GC = Geo<TH / 2, TW / 2>;
+    static constexpr bool GLR = MODE != MODE_BA, THR = MODE == MODE_X2;
+    static constexpr int zf = 0;
+    static constexpr int sA = zf + GF::floats(6);
+    static constexpr int sB = sA + (GLR ? GF::floats(2) : 0);
+    static constexpr int lA = sB + GF::floats(2);
+    static constexpr int oB = lA + (GLR ? GF::floats(1) : 0);
+    static constexpr int oT = oB + GF::floats(1);
+    static constexpr int pz = oT + (THR ? GF::floats(1) : 0);
+    static constexpr int sA1 = pz + GC::floats(3);
+    static constexpr int sB1 = sA1 + (GLR ? GC::floats(2) : 0);
+    static constexpr int lA1 = sB1 + GC::floats(2);
+    static constexpr int oB1 = lA1 + (GLR ? GC::floats(1) : 0);
+    static constexpr int oT1 = oB1 + GC::floats(1);
+    static constexpr int wL0 = oT1 + (THR ? GC::floats(1) : 0);
+    static constexpr int cR0 = wL0 + (GLR ? 4 * GF::floats(1) : 0);
+    static constexpr int cD0 = cR0 + GF::floats(2);
+    static constexpr int wT0 = cD0 + GF::floats(2);
+    static constexpr int wL1 = wT0 + (THR ? 4 * GF::floats(2) : 0);
+    static constexpr int cR1 = wL1 + (GLR ? 4 * GC::floats(1) : 0);
+    static constexpr int cD1 = cR1 + GC::floats(2);
+    static constexpr int wT1 = cD1 + GC::floats(2);
+    static constexpr int total = wT1 + (THR ? 4 * GC::floats(2) : 0);
 };
 
-template <int MODE, int TH, int TW>
-__global__ void __launch_bounds__(GLR_THREADS) k_block_stage(BlockFwdArgs a) {
+template <int MODE, int TH, int TW, int NT>
+__global__ void __launch_bounds__(NT) k_block_stage(BlockFwdArgs a) {
     GLR_SMEM_DECL(smem);
-    constexpr bool GLR = MODE != MODE_BA;  // BA only needs the GTV chain
-    constexpr bool THR = MODE == MODE_X2;  // thresholded right-hand side
-    const int H = a.s.H, W = a.s.W, Hc = H / 2, Wc = W / 2, F = a.s.F, G = a.s.G;
+    using LY = FwdLayout<MODE, TH, TW>;
+    using GF = typename LY::GF;
+    using GC = typename LY::GC;
+    constexpr bool GLR = LY::GLR, THR = LY::THR;
+    const int H = a.s.H, W = a.s.W, F = a.s.F, G = a.s.G;
     const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
     const int tile = blockIdx.x % (tiles_w * tiles_h), plane = blockIdx.x / (tiles_w * tiles_h);
     const int g = plane % G, b = plane / G;
-    const int h0 = (tile / tiles_w) * TH, w0 = (tile % tiles_w) * TW;
-    const int hc0 = h0 / 2, wc0 = w0 / 2;
-    const size_t HW = (size_t)H * W, HWc = (size_t)Hc * Wc;
+    GF gf; gf.H = H; gf.W = W; gf.h0 = (tile / tiles_w) * TH; gf.w0 = (tile % tiles_w) * TW;
+    GC gc; gc.H = H / 2; gc.W = W / 2; gc.h0 = gf.h0 / 2; gc.w0 = gf.w0 / 2;
+    const size_t HW = (size_t)H * W, HWc = HW / 4;
 
-    // ---- carve shared memory
-    float* cur = smem;
-    View zf = make_view(cur, h0 - 6, w0 - 6, TH + 12, TW + 12);
-    View sA = make_view(cur, h0 - 2, w0 - 2, TH + 4, TW + 4);
-    View sB = make_view(cur, h0 - 2, w0 - 2, TH + 4, TW + 4);
-    View lA = make_view(cur, h0 - 1, w0 - 1, TH + 2, TW + 2);
-    View oB = make_view(cur, h0 - 1, w0 - 1, TH + 2, TW + 2);
-    View oT = make_view(cur, h0 - 1, w0 - 1, TH + 2, TW + 2);
-    View pz = make_view(cur, hc0 - 3, wc0 - 3, TH / 2 + 6, TW / 2 + 6);
-    View sA1 = make_view(cur, hc0 - 2, wc0 - 2, TH / 2 + 4, TW / 2 + 4);
-    View sB1 = make_view(cur, hc0 - 2, wc0 - 2, TH / 2 + 4, TW / 2 + 4);
-    View lA1 = make_view(cur, hc0 - 1, wc0 - 1, TH / 2 + 2, TW / 2 + 2);
-    View oB1 = make_view(cur, hc0 - 1, wc0 - 1, TH / 2 + 2, TW / 2 + 2);
-    View oT1 = make_view(cur, hc0 - 1, wc0 - 1, TH / 2 + 2, TW / 2 + 2);
-    View tc = make_view(cur, hc0, wc0, TH / 2, TW / 2);
-    View tcT = make_view(cur, hc0, wc0, TH / 2, TW / 2);
-    WViews wL0 = make_wviews(cur, h0 - 1, w0 - 1, TH + 2, TW + 2);
-    WViews wT0 = make_wviews(cur, h0 - 2, w0 - 2, TH + 4, TW + 4);
-    WViews wL1 = make_wviews(cur, hc0 - 1, wc0 - 1, TH / 2 + 2, TW / 2 + 2);
-    WViews wT1 = make_wviews(cur, hc0 - 2, wc0 - 2, TH / 2 + 4, TW / 2 + 4);
+    auto zf = plane_at<GF, 6>(smem, LY::zf);
+    auto sA = plane_at<GF, 2>(smem, LY::sA);
+    auto sB = plane_at<GF, 2>(smem, LY::sB);
+    auto lA = plane_at<GF, 1>(smem, LY::lA);
+    auto oB = plane_at<GF, 1>(smem, LY::oB);
+    auto oT = plane_at<GF, 1>(smem, LY::oT);
+    auto pz = plane_at<GC, 3>(smem, LY::pz);
+    auto sA1 = plane_at<GC, 2>(smem, LY::sA1);
+    auto sB1 = plane_at<GC, 2>(smem, LY::sB1);
+    auto lA1 = plane_at<GC, 1>(smem, LY::lA1);
+    auto oB1 = plane_at<GC, 1>(smem, LY::oB1);
+    auto oT1 = plane_at<GC, 1>(smem, LY::oT1);
+    auto wL0 = wplanes_at<GF, 1>(smem, LY::wL0);
+    auto cR0 = plane_at<GF, 2>(smem, LY::cR0);
+    auto cD0 = plane_at<GF, 2>(smem, LY::cD0);
+    auto wT0 = wplanes_at<GF, 2>(smem, LY::wT0);
+    auto wL1 = wplanes_at<GC, 1>(smem, LY::wL1);
+    auto cR1 = plane_at<GC, 2>(smem, LY::cR1);
+    auto cD1 = plane_at<GC, 2>(smem, LY::cD1);
+    auto wT1 = wplanes_at<GC, 2>(smem, LY::wT1);
 
     // ---- per-graph scalars
     const float aT0 = expf(a.p.ro0[g]), aT1 = expf(a.p.ro1[g]);
@@ -88,15 +108,21 @@ __global__ void __launch_bounds__(GLR_THREADS) k_block_stage(BlockFwdArgs a) {
         beta2 = a.p.beta[2 * G + g];
         if (a.p.skip) { s0 = a.p.skip[0]; s1 = a.p.skip[1]; }
     }
+    const bool has_skip = MODE == MODE_X3 && a.p.skip != nullptr;
 
     // ---- weights of this graph (shared by its F channels)
     const size_t wplane = (size_t)plane * 4;
-    tile_load_weights(wT0, a.wT0 + wplane * HW, H, W);
-    tile_load_weights(wT1, a.wT1 + wplane * HWc, Hc, Wc);
-    if (GLR) {
-        tile_load_weights(wL0, a.wL0 + wplane * HW, H, W);
-        tile_load_weights(wL1, a.wL1 + wplane * HWc, Hc, Wc);
+    load_gtv_coeffs(gf, cR0, cD0, a.wT0 + wplane * HW);
+    load_gtv_coeffs(gc, cR1, cD1, a.wT1 + wplane * HWc);
+    if (THR) {
+        load_weights(gf, wT0, a.wT0 + wplane * HW);
+        load_weights(gc, wT1, a.wT1 + wplane * HWc);
     }
+    if (GLR) {
+        load_weights(gf, wL0, a.wL0 + wplane * HW);
+        load_weights(gc, wL1, a.wL1 + wplane * HWc);
+    }
+    const bool vec = (W & 3) == 0;
 
     for (int f = 0; f < F; ++f) {
         const int c = g * F + f;
@@ -105,58 +131,98 @@ __global__ void __launch_bounds__(GLR_THREADS) k_block_stage(BlockFwdArgs a) {
         StatsTaps kL0 = kT0, kL1 = kT1;
         if (GLR) { kL0 = glr_load_taps(a.p.glr0.stats, c); kL1 = glr_load_taps(a.p.glr1.stats, c); }
 
-        __syncthreads();  // previous channel's epilogue is done with the views
-        tile_load_clamped(zf, a.z + off, H, W);
+        __syncthreads();  // previous channel's epilogue is done with the planes
+        load_plane<true>(gf, zf, a.z + off);
         __syncthreads();
         // phase 1: S on the fine grid, pooling
-        if (GLR) tile_S2(sA, kL0, sB, kT0, zf, H, W);
-        else tile_S(sB, zf, kT0, H, W);
-        tile_pool(pz, zf, Hc, Wc);
+        stage_S<GLR>(gf, GLR ? sA : sB, GLR ? kL0 : kT0, sB, kT0, zf);
+        stage_pool(gc, pz, zf);
         __syncthreads();
         // phase 2: fine L / GTV cores, coarse S
-        if (GLR) tile_L(lA, sA, wL0, H, W);
-        tile_gtv_core<false>(oB, sB, wT0, 0.f, H, W);
-        if (THR) tile_gtv_core<true>(oT, sB, wT0, G0, H, W);
-        if (GLR) tile_S2(sA1, kL1, sB1, kT1, pz, Hc, Wc);
-        else tile_S(sB1, pz, kT1, Hc, Wc);
+        if (GLR) stage_L(gf, lA, sA, wL0);
+        stage_gtv_lin(gf, oB, sB, cR0, cD0);
+        if (THR) stage_gtv_thr(gf, oT, sB, wT0, G0);
+        stage_S<GLR>(gc, GLR ? sA1 : sB1, GLR ? kL1 : kT1, sB1, kT1, pz);
         __syncthreads();
         // phase 3: coarse cores
-        if (GLR) tile_L(lA1, sA1, wL1, Hc, Wc);
-        tile_gtv_core<false>(oB1, sB1, wT1, 0.f, Hc, Wc);
-        if (THR) tile_gtv_core<true>(oT1, sB1, wT1, G1, Hc, Wc);
+        if (GLR) stage_L(gc, lA1, sA1, wL1);
+        stage_gtv_lin(gc, oB1, sB1, cR1, cD1);
+        if (THR) stage_gtv_thr(gc, oT1, sB1, wT1, G1);
         __syncthreads();
-        // phase 4: coarse St, scaled
-        TILE_LOOP(i, tc.size()) {
-            int h = hc0 + i / tc.nw, w = wc0 + i % tc.nw;
-            float v = aT1 * tile_St_at(oB1, kT1, h, w);
-            if (GLR) v += aL1 * tile_St_at(lA1, kL1, h, w);
-            tc.p[i] = v;
-            if (THR) tcT.p[i] = aT1 * tile_St_at(oT1, kT1, h, w);
-        }
-        __syncthreads();
-        // phase 5: fine St + epilogue
-        TILE_LOOP(i, TH * TW) {
-            int h = h0 + i / TW, w = w0 + i % TW;
+        // phase 4: fine St (+ the two coarse St values under each quad) and the stage epilogue
+        TILE_LOOP(i, GF::items(0)) {
+            QUAD_ITEM(GF, 0, i, r, cq);
+            const int h = gf.h0 + r, w = gf.gw(cq);
             if (h >= H || w >= W) continue;
-            const size_t gi = off + (size_t)h * W + w;
-            const float zv = zf.at(h, w);
-            float Az = zv + aT0 * tile_St_at(oB, kT0, h, w) + 0.25f * tc.at(h >> 1, w >> 1);
-            if (GLR) Az += aL0 * tile_St_at(lA, kL0, h, w);
-            if (MODE == MODE_BA) {
-                a.out0[gi] = Az;  // y + R_lin(y)
-            } else if (MODE == MODE_X1) {
-                a.out0[gi] = zv + alpha * (zv - Az);
-            } else if (MODE == MODE_X2) {
-                float bB = a.y[gi] + aT0 * tile_St_at(oT, kT0, h, w) + 0.25f * tcT.at(h >> 1, w >> 1);
-                float r1 = bB - Az;
-                a.out1[gi] = bB;
-                a.out2[gi] = r1;
-                a.out0[gi] = zv + alpha * r1;
+            float zq[4], Az[4], rT[4];
+            ld4(zf.lrc(r + 6, cq), zq);
+            St_quad<GF::P>(oB.lrc(r + 1, cq), kT0, Az);
+            const int rc = (r >> 1) + 1, cc = (cq >> 1) + 4;   // coarse row (halo-1 planes) / column under this quad
+            float tc0 = aT1 * St_elem(oB1.lrc(rc, cc), GC::P, kT1), tc1 = aT1 * St_elem(oB1.lrc(rc, cc + 1), GC::P, kT1);
+            if (GLR) {
+                float gl_[4];
+                St_quad<GF::P>(lA.lrc(r + 1, cq), kL0, gl_);
+                tc0 += aL1 * St_elem(lA1.lrc(rc, cc), GC::P, kL1);
+                tc1 += aL1 * St_elem(lA1.lrc(rc, cc + 1), GC::P, kL1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) Az[j] = aT0 * Az[j] + aL0 * gl_[j];
             } else {
-                float r1 = a.r1_in[gi];
-                float u2 = (a.bB_in[gi] - Az) + beta2 * r1;
-                float x3 = zv + alpha * u2;
-                a.out0[gi] = a.p.skip ? s0 * a.y[gi] + s1 * x3 : x3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) Az[j] = aT0 * Az[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Az[j] += zq[j] + 0.25f * (j < 2 ? tc0 : tc1);
+            if (THR) {
+                St_quad<GF::P>(oT.lrc(r + 1, cq), kT0, rT);
+                const float t0 = aT1 * St_elem(oT1.lrc(rc, cc), GC::P, kT1), t1 = aT1 * St_elem(oT1.lrc(rc, cc + 1), GC::P, kT1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rT[j] = aT0 * rT[j] + 0.25f * (j < 2 ? t0 : t1);
+            }
+            const size_t gi = off + (size_t)h * W + w;
+            const bool full = vec && w + 3 < W;
+            float o0[4], o1[4], o2[4], in0[4], in1[4], in2[4];
+            // pointwise operands
+            if (MODE == MODE_X2 || MODE == MODE_X3) {
+                if (full) {
+                    if (MODE == MODE_X2 || has_skip) ld4(a.y + gi, in0);
+                    if (MODE == MODE_X3) { ld4(a.bB_in + gi, in1); ld4(a.r1_in + gi, in2); }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = w + j < W;
+                        in0[j] = ok && (MODE == MODE_X2 || has_skip) ? a.y[gi + j] : 0.f;
+                        in1[j] = ok && MODE == MODE_X3 ? a.bB_in[gi + j] : 0.f;
+                        in2[j] = ok && MODE == MODE_X3 ? a.r1_in[gi + j] : 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (MODE == MODE_BA) {
+                    o0[j] = Az[j];  // y + R_lin(y)
+                } else if (MODE == MODE_X1) {
+                    o0[j] = zq[j] + alpha * (zq[j] - Az[j]);
+                } else if (MODE == MODE_X2) {
+                    const float bB = in0[j] + rT[j], r1 = bB - Az[j];
+                    o1[j] = bB;
+                    o2[j] = r1;
+                    o0[j] = zq[j] + alpha * r1;
+                } else {
+                    const float u2 = (in1[j] - Az[j]) + beta2 * in2[j];
+                    const float x3 = zq[j] + alpha * u2;
+                    o0[j] = has_skip ? s0 * in0[j] + s1 * x3 : x3;
+                }
+            }
+            if (full) {
+                st4(a.out0 + gi, o0);
+                if (MODE == MODE_X2) { st4(a.out1 + gi, o1); st4(a.out2 + gi, o2); }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (w + j < W) {
+                        a.out0[gi + j] = o0[j];
+                        if (MODE == MODE_X2) { a.out1[gi + j] = o1[j]; a.out2[gi + j] = o2[j]; }
+                    }
             }
         }
     }
@@ -227,18 +293,20 @@ static int launch_stage(const BlockFwdArgs& a, void* stream) {
     const long tiles = (long)((s.W + GLR_TW - 1) / GLR_TW) * ((s.H + GLR_TH - 1) / GLR_TH);
     const long blocks = tiles * s.B * s.G;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
-    constexpr size_t smem = FwdSmem<GLR_TH, GLR_TW>::value * sizeof(float);
+    constexpr int NT = MODE == MODE_X2 ? 512 : 256;   // X2 holds both cores' planes: 1 CTA/SM, so give it more warps
+    constexpr size_t smem = (size_t)FwdLayout<MODE, GLR_TH, GLR_TW>::total * sizeof(float);
+    static_assert(smem <= 227 * 1024, "forward tile does not fit shared memory");
 #ifndef GLRGTV_EMU
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_block_stage<MODE, GLR_TH, GLR_TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(k_block_stage<MODE, GLR_TH, GLR_TW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return glr_record_launch_error();
         configured = true;
     }
 #endif
     GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_BA + MODE, stream);
-    GLR_LAUNCH((k_block_stage<MODE, GLR_TH, GLR_TW>), dim3((unsigned)blocks), GLR_THREADS, smem, stream, a);
+    GLR_LAUNCH((k_block_stage<MODE, GLR_TH, GLR_TW, NT>), dim3((unsigned)blocks), NT, smem, stream, a);
     GLR_PROF_END(GLRGTV_SLOT_FWD_BA + MODE, stream);
     return GLR_CHECK_LAUNCH();
 }
@@ -291,6 +359,10 @@ extern "C" int glrgtv_block_fwd(const glrgtv_shape* s, const glrgtv_block_params
     if (!sv) return GLRGTV_ERR_POINTER;
     float* need[9] = {sv->wT0, sv->wL0, sv->wT1, sv->wL1, sv->bA, sv->x1, sv->bB, sv->r1, sv->x2};
     for (int i = 0; i < 9; ++i) GLR_REQUIRE_PTR(need[i]);
+    // the float4 paths need 16-byte aligned tensors (true for any allocator; channel offsets keep it when W%4==0)
+    if (!glr_aligned16(x) || !glr_aligned16(out)) return GLRGTV_ERR_POINTER;
+    for (int i = 0; i < 9; ++i)
+        if (!glr_aligned16(need[i])) return GLRGTV_ERR_POINTER;
 
     glrgtv_shape sc = *s;
     sc.H /= 2; sc.W /= 2;
