@@ -39,10 +39,10 @@ struct BlockBwdArgs {
 };
 
 // shared-memory layout (floats) of one backward stage
-template <int MODE, int TH, int TW>
+template <int MODE, int TH, int TW, int NT>
 struct BwdLayout {
-    using GF = Geo<TH, TW>;
-    using GC = Geo<TH / 2, TW / 2>;
+    using GF = Geo<TH, TW, NT>;
+    using GC = Geo<TH / 2, TW / 2, NT>;
     static constexpr bool HAS_A = MODE != BWD_BA, HAS_R = MODE == BWD_X2 || MODE == BWD_BA, THR = MODE == BWD_X2;
     static constexpr int F6 = GF::floats(6), F2 = GF::floats(2), F1 = GF::floats(1);
     static constexpr int C3 = GC::floats(3), C2 = GC::floats(2), C1 = GC::floats(1);
@@ -100,16 +100,18 @@ struct BwdLayout {
 #define EPI_LOOP(i, n, first) for (int i = (int)threadIdx.x - (first); i >= 0 && i < (n); i += (1 << 20))
 #endif
 
-// the four stats-parameter sums from five tap products
-__device__ __forceinline__ void stats_acc(float* acc, float ac, float ar, float ad, float au, float al) {
-    acc[0] += ac;
-    acc[1] += ar - ac;
-    acc[2] += ad - ac;
-    acc[3] += 4.f * ac - ar - ad - au - al;
+// per-tap sums (c, R, D, U, L) of one stats kernel: acc[t] += g * v_t; they are turned into the four parameter
+// gradients (p01 = c, p02a = R - c, p02b = D - c, p03 = 4c - R - D - U - L) once per channel at commit time
+__device__ __forceinline__ void stats_acc(float* acc, float g, float vc, float vr, float vd, float vu, float vl) {
+    acc[0] += g * vc;
+    acc[1] += g * vr;
+    acc[2] += g * vd;
+    acc[3] += g * vu;
+    acc[4] += g * vl;
 }
 
 // Parameter-gradient work of one epilogue quad at one resolution (fine: z halo 6, coarse: z halo 3).
-//   st   : [T: p01,p02a,p02b,p03 | L: ...]  per-channel stats sums of this resolution's two modules
+//   st   : [T: c,R,D,U,L | L: c,R,D,U,L]    per-channel tap sums of this resolution's two modules
 //   sums : [mu, ro, gamma]                  per-graph sums of this resolution
 //   acc  : [L e0..e3][4] then [T e0..e3][4] edge-weight gradient accumulators of this quad
 // returns the forward St values (glr, gtv_lin) and the S-adjoint values VT+VL in V.
@@ -137,7 +139,7 @@ struct QuadWork {
         for (int j = 0; j < 4; ++j) {
             gtv_lin[j] = kT.kc * n.c[j] + kT.kr * n.L(j) + kT.kd * n.u[j] + kT.ku * n.d[j] + kT.kl * n.Rr(j);
             const float gu = aT * ((HAS_A ? ga[j] : 0.f) + (HAS_R && !THR ? gb[j] : 0.f));
-            stats_acc(st, gu * n.c[j], gu * n.L(j), gu * n.u[j], gu * n.d[j], gu * n.Rr(j));
+            stats_acc(st, gu, n.c[j], n.L(j), n.u[j], n.d[j], n.Rr(j));
             gtv_R[j] = gtv_lin[j];
         }
         if (THR) {
@@ -146,7 +148,7 @@ struct QuadWork {
             for (int j = 0; j < 4; ++j) {
                 gtv_R[j] = kT.kc * n.c[j] + kT.kr * n.L(j) + kT.kd * n.u[j] + kT.ku * n.d[j] + kT.kl * n.Rr(j);
                 const float gu = aT * gb[j];
-                stats_acc(st, gu * n.c[j], gu * n.L(j), gu * n.u[j], gu * n.d[j], gu * n.Rr(j));
+                stats_acc(st, gu, n.c[j], n.L(j), n.u[j], n.d[j], n.Rr(j));
             }
         }
         N5 nz;
@@ -161,7 +163,7 @@ struct QuadWork {
             if (w + j == 0) self += kT.kl;
             V[j] = (kT.kc + self) * n.c[j] + kT.kr * n.L(j) + kT.kd * n.u[j] + kT.ku * n.d[j] + kT.kl * n.Rr(j);
             const float gs = n.c[j];
-            stats_acc(st, gs * nz.c[j], gs * nz.Rr(j), gs * nz.d[j], gs * nz.u[j], gs * nz.L(j));
+            stats_acc(st, gs, nz.c[j], nz.Rr(j), nz.d[j], nz.u[j], nz.L(j));
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -175,7 +177,7 @@ struct QuadWork {
             for (int j = 0; j < 4; ++j) {
                 glr[j] = kL.kc * n.c[j] + kL.kr * n.L(j) + kL.kd * n.u[j] + kL.ku * n.d[j] + kL.kl * n.Rr(j);
                 const float gu = aL * ga[j];
-                stats_acc(st + 4, gu * n.c[j], gu * n.L(j), gu * n.u[j], gu * n.d[j], gu * n.Rr(j));
+                stats_acc(st + 5, gu, n.c[j], n.L(j), n.u[j], n.d[j], n.Rr(j));
                 sums[0] += gu * glr[j];
             }
             ld_n5<P>(gsL.lrc(r + 1, c), n);
@@ -188,7 +190,7 @@ struct QuadWork {
                 if (w + j == 0) self += kL.kl;
                 V[j] += (kL.kc + self) * n.c[j] + kL.kr * n.L(j) + kL.kd * n.u[j] + kL.ku * n.d[j] + kL.kl * n.Rr(j);
                 const float gs = n.c[j];
-                stats_acc(st + 4, gs * nz.c[j], gs * nz.Rr(j), gs * nz.d[j], gs * nz.u[j], gs * nz.L(j));
+                stats_acc(st + 5, gs, nz.c[j], nz.Rr(j), nz.d[j], nz.u[j], nz.L(j));
             }
             // edge weights of L: gw_e -= gl * sA[n_e]
             float glq[4];
@@ -270,7 +272,7 @@ __device__ __forceinline__ void warp_commit(float* vals, float* sh) {
 template <int MODE, int TH, int TW, int NT>
 __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
     GLR_SMEM_DECL(smem);
-    using LY = BwdLayout<MODE, TH, TW>;
+    using LY = BwdLayout<MODE, TH, TW, NT>;
     using GF = typename LY::GF;
     using GC = typename LY::GC;
     constexpr bool HAS_A = LY::HAS_A, HAS_R = LY::HAS_R, THR = LY::THR;
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
     auto cR1 = plane_at<GC, 2>(smem, LY::cR1);
     auto cD1 = plane_at<GC, 2>(smem, LY::cD1);
     auto wT1 = wplanes_at<GC, 2>(smem, LY::wT1);
-    float* red = smem + LY::red;  // [0:16) per-channel stats sums, [16:26) per-graph sums
+    float* red = smem + LY::red;  // [0:20) per-channel tap sums, [32:42) per-graph sums
 
     // ---- per-graph scalars
     const float aT0 = expf(a.p.ro0[g]), aT1 = expf(a.p.ro1[g]);
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
         load_weights(gf, wL0, a.wL0 + wplane * HW);
         load_weights(gc, wL1, a.wL1 + wplane * HWc);
     }
-    TILE_LOOP(i, 32) red[i] = 0.f;
+    TILE_LOOP_NT(NT, i, 64) red[i] = 0.f;
 
     // edge-weight gradient accumulators of this thread's epilogue quad: [L e][4] + [T e][4]
     ACC_DECL(accF, NQF, 32);
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
         __syncthreads();
         // ---- phase 0: stage input (clamp-extended) and upstream gradients (zero-extended)
         load_plane<true>(gf, zf, a.z + off);
-        TILE_LOOP(i, GF::items(6)) {
+        TILE_LOOP_NT(NT, i, GF::items(6)) {
             QUAD_ITEM(GF, 6, i, r, cq);
             const int h = gf.gh(r, 6), w = gf.gw(cq);
             float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -455,7 +457,9 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
             __syncthreads();
         }
         // ---- phase 4: epilogues.  Threads [0, NQF) own one fine quad each, threads [NQF, NQF+NQC) one coarse quad.
-        float stF[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, stC[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float stF[10], stC[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) stF[k] = stC[k] = 0.f;
         EPI_LOOP(i, NQC, NQF) {
             QUAD_ITEM(GC, 0, i, r, cq);
             const int h = gc.h0 + r, w = gc.gw(cq);
@@ -538,18 +542,21 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
             }
         }
         // ---- per-channel stats gradients: warp shuffles -> shared atomics -> one global atomic per value
-        warp_commit<8>(stF, red);
-        warp_commit<8>(stC, red + 8);
+        warp_commit<10>(stF, red);
+        warp_commit<10>(stC, red + 10);
         __syncthreads();
         {
             float* dst[4] = {a.gr.gtv0_stats, a.gr.glr0_stats, a.gr.gtv1_stats, a.gr.glr1_stats};
             const int C = G * F;
-            TILE_LOOP(t, 16) {   // red: fine [T0 | L0], coarse [T1 | L1], 4 values each
-                const int m = ((t >> 3) << 1) | ((t >> 2) & 1), k = t & 3;
-                if (HAS_A || m == 0 || m == 2) atomicAdd(&dst[m][k * C + c], red[t]);
-                red[t] = 0.f;
+            TILE_LOOP_NT(NT, t, 16) {   // red: [T0 | L0 | T1 | L1] x (c, R, D, U, L)
+                const int m = t >> 2, k = t & 3;
+                const float* q = red + 5 * m;
+                const float v = k == 0 ? q[0] : k == 1 ? q[1] - q[0] : k == 2 ? q[2] - q[0] : 4.f * q[0] - q[1] - q[2] - q[3] - q[4];
+                if (HAS_A || m == 0 || m == 2) atomicAdd(&dst[m][k * C + c], v);
             }
         }
+        __syncthreads();
+        TILE_LOOP_NT(NT, t, 20) red[t] = 0.f;
     }
 
     // ---- edge-weight gradients of this tile: one read-modify-write per stage
@@ -605,11 +612,11 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
     }
     // ---- per-graph scalar gradients
     __syncthreads();
-    warp_commit<7>(gsF, red + 16);
-    warp_commit<3>(gsC, red + 23);
+    warp_commit<7>(gsF, red + 32);
+    warp_commit<3>(gsC, red + 39);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const float* s = red + 16;  // mu0, ro0, gamma0, alpha_k, beta2, skip0, skip1, mu1, ro1, gamma1
+        const float* s = red + 32;  // mu0, ro0, gamma0, alpha_k, beta2, skip0, skip1, mu1, ro1, gamma1
         if (HAS_A) {
             atomicAdd(&a.gr.mu0[g], s[0]);
             atomicAdd(&a.gr.mu1[g], s[7]);
@@ -648,7 +655,7 @@ static int launch_bwd_stage(const BlockBwdArgs& a, void* stream) {
     const long tiles = (long)((s.W + GLR_BTW - 1) / GLR_BTW) * ((s.H + GLR_BTH - 1) / GLR_BTH);
     const long blocks = tiles * s.B * s.G;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
-    constexpr size_t smem = (size_t)BwdLayout<MODE, GLR_BTH, GLR_BTW>::total * sizeof(float);
+    constexpr size_t smem = (size_t)BwdLayout<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS>::total * sizeof(float);
     static_assert(smem <= 227 * 1024, "backward tile does not fit shared memory");
 #ifndef GLRGTV_EMU
     static bool configured = false;
@@ -666,10 +673,10 @@ static int launch_bwd_stage(const BlockBwdArgs& a, void* stream) {
     return GLR_CHECK_LAUNCH();
 }
 
-// strided edge-weight backward (ops_basic.cu)
-int glr_edge_weights_bwd_strided(const glrgtv_shape* s, const glrgtv_window* win, const float* feat, size_t feat_bs,
-                                 const float* multiM, const float* w, const float* gw, float* gfeat, size_t gfeat_bs,
-                                 float* gmultiM, float* scratch, void* stream);
+// tiled edge-weight backward of one resolution (block_weights_bwd.cu)
+int glr_block_weights_bwd(const glrgtv_shape* s, const float* feat, const float* M_gtv, const float* M_glr,
+                          const float* w_gtv, const float* w_glr, const float* gw_gtv, const float* gw_glr, float* gfeat,
+                          float* gM_gtv, float* gM_glr, void* stream);
 
 // workspace layout in floats; every segment starts 16-byte aligned
 static size_t ws_floats(const glrgtv_shape* s, size_t* o_gx2, size_t* o_gx1, size_t* o_gbA, size_t* o_gw, size_t* o_scr) {
@@ -680,7 +687,7 @@ static size_t ws_floats(const glrgtv_shape* s, size_t* o_gx2, size_t* o_gx1, siz
     *o_gx1 = off; off = up(off + C * N);
     *o_gbA = off; off = up(off + C * N);
     *o_gw = off;  off = up(off + 2 * GE * N + 2 * GE * (N / 4));
-    *o_scr = off; off = up(off + (size_t)s->G * 5 * N);
+    *o_scr = off;
     return off;
 }
 
@@ -731,24 +738,15 @@ extern "C" int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params
     a.z = x; a.gin = ws + o_gbA; a.gz_out = gx;
     if ((rc = launch_bwd_stage<BWD_BA>(a, stream))) return rc;
 
-    // edge weights -> features (four sets; feat halves are strided in the batch dimension)
-    glrgtv_window win;
-    win.n_edges = 4;
-    const int dh[4] = {-1, 0, 0, 1}, dw[4] = {0, -1, 1, 0};
-    for (int e = 0; e < 4; ++e) { win.dh[e] = dh[e]; win.dw[e] = dw[e]; }
+    // edge weights -> features: one launch per resolution covers both operator families
     glrgtv_shape sc = *s;
     sc.H /= 2; sc.W /= 2;
-    const size_t C = (size_t)s->G * s->F, HW = (size_t)s->H * s->W, HWc = HW / 4;
-    float* scr = ws + o_scr;
+    (void)o_scr;
     GLR_PROF_BEGIN(GLRGTV_SLOT_BWD_WEIGHTS, stream);
-    if ((rc = glr_edge_weights_bwd_strided(s, &win, feat0, 2 * C * HW, p->gtv0.multiM, sv->wT0, a.gwT0, gfeat0,
-                                           2 * C * HW, gr->gtv0_M, scr, stream))) return rc;
-    if ((rc = glr_edge_weights_bwd_strided(s, &win, feat0 + C * HW, 2 * C * HW, p->glr0.multiM, sv->wL0, a.gwL0,
-                                           gfeat0 + C * HW, 2 * C * HW, gr->glr0_M, scr, stream))) return rc;
-    if ((rc = glr_edge_weights_bwd_strided(&sc, &win, feat1, 2 * C * HWc, p->gtv1.multiM, sv->wT1, a.gwT1, gfeat1,
-                                           2 * C * HWc, gr->gtv1_M, scr, stream))) return rc;
-    rc = glr_edge_weights_bwd_strided(&sc, &win, feat1 + C * HWc, 2 * C * HWc, p->glr1.multiM, sv->wL1, a.gwL1,
-                                      gfeat1 + C * HWc, 2 * C * HWc, gr->glr1_M, scr, stream);
+    if ((rc = glr_block_weights_bwd(s, feat0, p->gtv0.multiM, p->glr0.multiM, sv->wT0, sv->wL0, a.gwT0, a.gwL0, gfeat0,
+                                    gr->gtv0_M, gr->glr0_M, stream))) return rc;
+    rc = glr_block_weights_bwd(&sc, feat1, p->gtv1.multiM, p->glr1.multiM, sv->wT1, sv->wL1, a.gwT1, a.gwL1, gfeat1,
+                               gr->gtv1_M, gr->glr1_M, stream);
     GLR_PROF_END(GLRGTV_SLOT_BWD_WEIGHTS, stream);
     return rc;
 }

@@ -32,10 +32,10 @@ struct BlockFwdArgs {
 };
 
 // shared-memory layout (floats) of one forward stage
-template <int MODE, int TH, int TW>
+template <int MODE, int TH, int TW, int NT>
 struct FwdLayout {
-    using GF = Geo<TH, TW>;
-    using GC = Geo<TH / 2, TW / 2>;
+    using GF = Geo<TH, TW, NT>;
+    using GC = Geo<TH / 2, TW / 2, NT>;
     static constexpr bool GLR = MODE != MODE_BA, THR = MODE == MODE_X2;
     static constexpr int zf = 0;
     static constexpr int sA = zf + GF::floats(6);
@@ -63,7 +63,7 @@ struct FwdLayout {
 template <int MODE, int TH, int TW, int NT>
 __global__ void __launch_bounds__(NT) k_block_stage(BlockFwdArgs a) {
     GLR_SMEM_DECL(smem);
-    using LY = FwdLayout<MODE, TH, TW>;
+    using LY = FwdLayout<MODE, TH, TW, NT>;
     using GF = typename LY::GF;
     using GC = typename LY::GC;
     constexpr bool GLR = LY::GLR, THR = LY::THR;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NT) k_block_stage(BlockFwdArgs a) {
         if (THR) stage_gtv_thr(gc, oT1, sB1, wT1, G1);
         __syncthreads();
         // phase 4: fine St (+ the two coarse St values under each quad) and the stage epilogue
-        TILE_LOOP(i, GF::items(0)) {
+        TILE_LOOP_NT(NT, i, GF::items(0)) {
             QUAD_ITEM(GF, 0, i, r, cq);
             const int h = gf.h0 + r, w = gf.gw(cq);
             if (h >= H || w >= W) continue;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(GLR_THREADS) k_block_weights(glrgtv_shape s, c
     const float* Mg = (set ? M_glr : M_gtv) + g * F;
     float* wp = (set ? w_glr : w_gtv) + ((size_t)b * G + g) * 4 * HW;
     // phase 1: normalised, scaled features on the tile (+) 1 (clamp-extended), layout ft[f][pixel]
-    TILE_LOOP(i, NP) {
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) {
         int h = glr_clampi(h0 - 1 + i / NW, 0, H - 1), w = glr_clampi(w0 - 1 + i % NW, 0, W - 1);
         const float* q = fp + (size_t)h * W + w;
         float n2 = 0.f;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(GLR_THREADS) k_block_weights(glrgtv_shape s, c
     }
     __syncthreads();
     // phase 2: similarities with the four neighbours, softmax
-    TILE_LOOP(i, TH * TW) {
+    for (int i = threadIdx.x; i < TH * TW; i += blockDim.x) {
         int lh = i / TW, lw = i % TW, h = h0 + lh, w = w0 + lw;
         if (h >= H || w >= W) continue;
         const float* c = smem + (lh + 1) * NW + (lw + 1);
@@ -294,7 +294,7 @@ static int launch_stage(const BlockFwdArgs& a, void* stream) {
     const long blocks = tiles * s.B * s.G;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
     constexpr int NT = MODE == MODE_X2 ? 512 : 256;   // X2 holds both cores' planes: 1 CTA/SM, so give it more warps
-    constexpr size_t smem = (size_t)FwdLayout<MODE, GLR_TH, GLR_TW>::total * sizeof(float);
+    constexpr size_t smem = (size_t)FwdLayout<MODE, GLR_TH, GLR_TW, NT>::total * sizeof(float);
     static_assert(smem <= 227 * 1024, "forward tile does not fit shared memory");
 #ifndef GLRGTV_EMU
     static bool configured = false;

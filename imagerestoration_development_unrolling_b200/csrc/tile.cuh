@@ -25,13 +25,22 @@ struct alignas(8) float2 { float x, y; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 #endif
 
-#define TILE_LOOP(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
+// Item loops.  The CTA size NT is a compile-time constant carried by the geometry type, so trip counts are known
+// and the loops unroll: the independent items of one thread interleave, which is where the ILP comes from.
+// (Emulation build: one thread walks all items.)
+#ifdef GLRGTV_EMU
+#define TILE_LOOP_NT(NT, i, n) for (int i = 0; i < (n); ++i)
+#else
+#define TILE_LOOP_NT(NT, i, n) \
+    _Pragma("unroll") for (int k_##i = 0, i = threadIdx.x; k_##i < ((n) + (NT)-1) / (NT); ++k_##i, i += (NT)) if (i < (n))
+#endif
+#define TILE_LOOP(i, n) TILE_LOOP_NT(G::NT, i, n)
 #define COL0 8  // local column of the tile's first pixel
 
 // geometry of one resolution of a tile: image size, tile origin (global), tile size
-template <int TR_, int TC_>
+template <int TR_, int TC_, int NT_>
 struct Geo {
-    static constexpr int TR = TR_, TC = TC_, P = TC_ + 16;
+    static constexpr int TR = TR_, TC = TC_, P = TC_ + 16, NT = NT_;
     int H, W, h0, w0;
     // quads [q0, q1) cover local columns [COL0 - R, COL0 + TC + R)
     static constexpr int q0(int R) { return (COL0 - R) / 4; }
@@ -148,7 +157,7 @@ __device__ __forceinline__ void stage_S(const G& g, const Plane<G, RD>& dA, cons
 // 2x2 mean: fine clamp-extended src (halo 2*RD) -> coarse clamp-extended dst (halo RD)
 template <class GC, class GF, int RD>
 __device__ __forceinline__ void stage_pool(const GC& gc, const Plane<GC, RD>& dst, const Plane<GF, 2 * RD>& src) {
-    TILE_LOOP(i, GC::items(RD)) {
+    TILE_LOOP_NT(GC::NT, i, GC::items(RD)) {
         QUAD_ITEM(GC, RD, i, r, c);
         const int h = gc.gh(r, RD), w = gc.gw(c);
         float v[4];
@@ -528,7 +537,7 @@ static inline int glr_aligned16(const void* p) { return (((uintptr_t)p) & 15u) =
 // zero-extended 2x2 mean of a zero-extended fine plane (VJP of P^T is P): coarse halo RD from fine halo 2*RD
 template <class GC, class GF, int RD>
 __device__ __forceinline__ void stage_pool_zero(const GC& gc, const Plane<GC, RD>& dst, const Plane<GF, 2 * RD>& src) {
-    TILE_LOOP(i, GC::items(RD)) {
+    TILE_LOOP_NT(GC::NT, i, GC::items(RD)) {
         QUAD_ITEM(GC, RD, i, r, c);
         const int h = gc.gh(r, RD), w = gc.gw(c);
         float v[4];
