@@ -38,18 +38,18 @@ struct BlockBwdArgs {
     float* gz_out;
 };
 
-// shared-memory layout (floats) of one backward stage
+// shared-memory layout (floats) of one backward stage (4 guard floats on either side, see FwdLayout)
 template <int MODE, int TH, int TW, int NT>
 struct BwdLayout {
     using GF = Geo<TH, TW, NT>;
     using GC = Geo<TH / 2, TW / 2, NT>;
     static constexpr bool HAS_A = MODE != BWD_BA, HAS_R = MODE == BWD_X2 || MODE == BWD_BA, THR = MODE == BWD_X2;
-    static constexpr int F6 = GF::floats(6), F2 = GF::floats(2), F1 = GF::floats(1);
+    static constexpr int F3 = GF::floats(3), F2 = GF::floats(2), F1 = GF::floats(1);
     static constexpr int C3 = GC::floats(3), C2 = GC::floats(2), C1 = GC::floats(1);
-    static constexpr int zf = 0;
-    static constexpr int gA = zf + F6;
-    static constexpr int gB = gA + (HAS_A ? F6 : 0);
-    static constexpr int sA = gB + (HAS_R ? F6 : 0);
+    static constexpr int zf = 4;
+    static constexpr int gA = zf + F3;
+    static constexpr int gB = gA + (HAS_A ? F3 : 0);
+    static constexpr int sA = gB + (HAS_R ? F3 : 0);
     static constexpr int sB = sA + (HAS_A ? F2 : 0);
     static constexpr int gl = sB + F2;
     static constexpr int goA = gl + (HAS_A ? F2 : 0);
@@ -82,7 +82,7 @@ struct BwdLayout {
     static constexpr int cR1 = wL1 + (HAS_A ? 4 * C2 : 0);
     static constexpr int cD1 = cR1 + (THR ? 0 : C2);
     static constexpr int wT1 = cD1 + (THR ? 0 : C2);
-    static constexpr int red = wT1 + (THR ? 4 * C2 : 0);
+    static constexpr int red = wT1 + (THR ? 4 * C2 : 0) + 4;
     static constexpr int total = red + 64;
 };
 
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
     using GF = typename LY::GF;
     using GC = typename LY::GC;
     constexpr bool HAS_A = LY::HAS_A, HAS_R = LY::HAS_R, THR = LY::THR;
-    constexpr int NQF = GF::items(0), NQC = GC::items(0);   // epilogue quads: fine / coarse
+    constexpr int NQF = GF::TR * (GF::NQ - 2), NQC = GC::TR * (GC::NQ - 2);   // epilogue quads: fine / coarse
     static_assert(NT >= NQF + NQC, "one epilogue quad per thread");
     const int H = a.s.H, W = a.s.W, F = a.s.F, G = a.s.G;
     const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
@@ -287,9 +287,9 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
     const size_t HW = (size_t)H * W, HWc = HW / 4;
     const bool vec = (W & 3) == 0, vecc = (gc.W & 3) == 0;
 
-    auto zf = plane_at<GF, 6>(smem, LY::zf);
-    auto gA = plane_at<GF, 6>(smem, LY::gA);
-    auto gB = plane_at<GF, 6>(smem, LY::gB);
+    auto zf = plane_at<GF, 3>(smem, LY::zf);
+    auto gA = plane_at<GF, 3>(smem, LY::gA);
+    auto gB = plane_at<GF, 3>(smem, LY::gB);
     auto sA = plane_at<GF, 2>(smem, LY::sA);
     auto sB = plane_at<GF, 2>(smem, LY::sB);
     auto gl = plane_at<GF, 2>(smem, LY::gl);
@@ -368,101 +368,66 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
         const StatsTaps kL0 = glr_load_taps(a.p.glr0.stats, c), kL1 = glr_load_taps(a.p.glr1.stats, c);
 
         __syncthreads();
-        // ---- phase 0: stage input (clamp-extended) and upstream gradients (zero-extended)
-        load_plane<true>(gf, zf, a.z + off);
-        TILE_LOOP_NT(NT, i, GF::items(6)) {
-            QUAD_ITEM(GF, 6, i, r, cq);
-            const int h = gf.gh(r, 6), w = gf.gw(cq);
-            float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
-            float q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f};
-            const size_t gi = off + (size_t)h * W + w;
-            constexpr bool need0 = MODE == BWD_X3 || MODE == BWD_X2, need1 = MODE != BWD_X3;   // gout / gin
-            if (vec && gf.quad_inside(h, w)) {
-                if (need0) ld4(a.gout + gi, q0);
-                if (need1) ld4(a.gin + gi, q1);
+        // ---- phase 0: stage input (clamp-extended) and upstream gradients (zero-extended), fine (+)3 and pooled
+        load_fine_and_pooled<true>(gf, gc, zf, pz, a.z + off, (const float*)nullptr, [](float v, float) { return v; });
+        if (MODE == BWD_X3) {
+            load_fine_and_pooled<false>(gf, gc, gA, gcA, a.gout + off, (const float*)nullptr, [=](float go, float) { return -c23 * go; });
+        } else if (MODE == BWD_X2) {
+            load_fine_and_pooled<false>(gf, gc, gA, gcA, a.gout + off, a.gin + off,
+                                        [=](float go, float gx2) { return -(be2 * c23 * go + al1 * gx2); });
+            load_fine_and_pooled<false>(gf, gc, gB, gcB, a.gout + off, a.gin + off,
+                                        [=](float go, float gx2) { return c23 * go + (be2 * c23 * go + al1 * gx2); });
+        } else if (MODE == BWD_X1) {
+            load_fine_and_pooled<false>(gf, gc, gA, gcA, a.gin + off, (const float*)nullptr, [=](float gx1, float) { return -al0 * gx1; });
+        } else {
+            load_fine_and_pooled<false>(gf, gc, gB, gcB, a.gin + off, (const float*)nullptr, [](float v, float) { return v; });
+        }
+        __syncthreads();
+        // ---- phase 1: forward S and the St-adjoints of the upstreams, both resolutions
+        TILE_LOOP_NT(NT, i, GF::items(2)) {
+            const Quad q = quad_of<GF, 2>(gf, i);
+            q_S<HAS_A>(gf, q, HAS_A ? sA : sB, HAS_A ? kL0 : kT0, sB, kT0, zf);
+            if (HAS_A) q_Szero<true, true>(gf, q, gl, kL0, aL0, goA, kT0, aT0, gA);
+            if (HAS_R) q_Szero<false, true>(gf, q, goB, kT0, 0.f, goB, kT0, aT0, gB);
+        }
+        TILE_LOOP_NT(NT, i, GC::items(2)) {
+            const Quad q = quad_of<GC, 2>(gc, i);
+            q_S<HAS_A>(gc, q, HAS_A ? sA1 : sB1, HAS_A ? kL1 : kT1, sB1, kT1, pz);
+            if (HAS_A) q_Szero<true, true>(gc, q, gl1, kL1, aL1, goA1, kT1, aT1, gcA);
+            if (HAS_R) q_Szero<false, true>(gc, q, goB1, kT1, 0.f, goB1, kT1, aT1, gcB);
+        }
+        __syncthreads();
+        // ---- phase 2: forward cores and adjoint cores, both resolutions
+        TILE_LOOP_NT(NT, i, GF::items(1)) {
+            const Quad q = quad_of<GF, 1>(gf, i);
+            if (HAS_A) { q_L(gf, q, lA, sA, wL0); q_L_adj(gf, q, gsL, gl, wL0); }
+            if (THR) {
+                q_gtv_raw<true, true>(gf, q, oB, oT, sB, wT0, G0);
+                q_gtv_raw_adj<true, true>(gf, q, gsT, goA, goB, sB, wT0, G0);
             } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (gf.inside(h, w + j)) {
-                        if (need0) q0[j] = a.gout[gi + j];
-                        if (need1) q1[j] = a.gin[gi + j];
-                    }
+                q_gtv_lin(gf, q, oB, sB, cR0, cD0);
+                q_gtv_lin(gf, q, gsT, HAS_A ? goA : goB, cR0, cD0);   // the linear core is self-adjoint
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (MODE == BWD_X3) va[j] = -c23 * q0[j];
-                else if (MODE == BWD_X2) {
-                    const float gr2 = c23 * q0[j], gr1 = be2 * gr2 + al1 * q1[j];
-                    va[j] = -gr1;
-                    vb[j] = gr2 + gr1;
-                } else if (MODE == BWD_X1) va[j] = -al0 * q1[j];
-                else vb[j] = q1[j];
+        }
+        TILE_LOOP_NT(NT, i, GC::items(1)) {
+            const Quad q = quad_of<GC, 1>(gc, i);
+            if (HAS_A) { q_L(gc, q, lA1, sA1, wL1); q_L_adj(gc, q, gsL1, gl1, wL1); }
+            if (THR) {
+                q_gtv_raw<true, true>(gc, q, oB1, oT1, sB1, wT1, G1);
+                q_gtv_raw_adj<true, true>(gc, q, gsT1, goA1, goB1, sB1, wT1, G1);
+            } else {
+                q_gtv_lin(gc, q, oB1, sB1, cR1, cD1);
+                q_gtv_lin(gc, q, gsT1, HAS_A ? goA1 : goB1, cR1, cD1);
             }
-            if (HAS_A) st4(gA.lrc(r, cq), va);
-            if (HAS_R) st4(gB.lrc(r, cq), vb);
         }
         __syncthreads();
-        // ---- phase 1: forward S + pooling; adjoint of St on the upstreams; pooled upstreams
-        stage_S<HAS_A>(gf, HAS_A ? sA : sB, HAS_A ? kL0 : kT0, sB, kT0, zf);
-        stage_pool(gc, pz, zf);
-        if (HAS_A) {
-            stage_Szero<false>(gf, gl, gA, kL0, aL0);
-            stage_Szero<true>(gf, goA, gA, kT0, aT0);
-            stage_pool_zero(gc, gcA, gA);
-        }
-        if (HAS_R) {
-            stage_Szero<true>(gf, goB, gB, kT0, aT0);
-            stage_pool_zero(gc, gcB, gB);
-        }
-        __syncthreads();
-        // ---- phase 2: forward cores (fine), coarse S; adjoint cores (fine), coarse St-adjoints
-        if (HAS_A) stage_L(gf, lA, sA, wL0);
-        if (THR) {
-            stage_gtv_lin_raw(gf, oB, sB, wT0);
-            stage_gtv_thr(gf, oT, sB, wT0, G0);
-        } else {
-            stage_gtv_lin(gf, oB, sB, cR0, cD0);
-        }
-        stage_S<HAS_A>(gc, HAS_A ? sA1 : sB1, HAS_A ? kL1 : kT1, sB1, kT1, pz);
-        if (HAS_A) {
-            stage_L_adj(gf, gsL, gl, wL0);
-            if (THR) stage_gtv_lin_raw(gf, gsT, goA, wT0);   // the linear core is self-adjoint
-            else stage_gtv_lin(gf, gsT, goA, cR0, cD0);
-            stage_Szero<false>(gc, gl1, gcA, kL1, aL1);
-            stage_Szero<true>(gc, goA1, gcA, kT1, aT1);
-        } else {
-            stage_gtv_lin(gf, gsT, goB, cR0, cD0);
-        }
-        if (HAS_R) stage_Szero<true>(gc, goB1, gcB, kT1, aT1);
-        __syncthreads();
-        // ---- phase 3: the thresholded adjoint adds into gsT; coarse cores, forward and adjoint
-        if (THR) stage_gtv_thr_adj_add(gf, gsT, goB, sB, wT0, G0);
-        if (HAS_A) stage_L(gc, lA1, sA1, wL1);
-        if (THR) {
-            stage_gtv_lin_raw(gc, oB1, sB1, wT1);
-            stage_gtv_thr(gc, oT1, sB1, wT1, G1);
-        } else {
-            stage_gtv_lin(gc, oB1, sB1, cR1, cD1);
-        }
-        if (HAS_A) {
-            stage_L_adj(gc, gsL1, gl1, wL1);
-            if (THR) stage_gtv_lin_raw(gc, gsT1, goA1, wT1);
-            else stage_gtv_lin(gc, gsT1, goA1, cR1, cD1);
-        } else {
-            stage_gtv_lin(gc, gsT1, goB1, cR1, cD1);
-        }
-        __syncthreads();
-        if (THR) {   // (needs the linear part of gsT1 complete)
-            stage_gtv_thr_adj_add(gc, gsT1, goB1, sB1, wT1, G1);
-            __syncthreads();
-        }
-        // ---- phase 4: epilogues.  Threads [0, NQF) own one fine quad each, threads [NQF, NQF+NQC) one coarse quad.
+        // ---- phase 3: epilogues.  Threads [0, NQF) own one fine quad each, threads [NQF, NQF+NQC) one coarse quad.
         float stF[10], stC[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) stF[k] = stC[k] = 0.f;
         EPI_LOOP(i, NQC, NQF) {
-            QUAD_ITEM(GC, 0, i, r, cq);
-            const int h = gc.h0 + r, w = gc.gw(cq);
+            const Quad qd = tile_quad_of(gc, i);
+            const int r = qd.r, cq = qd.c, h = qd.h, w = qd.w;
             if (h >= gc.H || w >= gc.W) continue;
             QuadWork<MODE, GC, 3> qw{gc, pz, sA1, sB1, gl1, goA1, goB1, lA1, oB1, oT1, gsL1, gsT1,
                                      a.wT1 + wplane * HWc, kT1, kL1, aT1, aL1, G1};
@@ -472,17 +437,17 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
             qw.run(r, cq, ga, gb, stC, gsC, ACC_PTR(accC, i, 32), V, glr, gtvl);
         }
         EPI_LOOP(i, NQF, 0) {
-            QUAD_ITEM(GF, 0, i, r, cq);
-            const int h = gf.h0 + r, w = gf.gw(cq);
+            const Quad qd = tile_quad_of(gf, i);
+            const int r = qd.r, cq = qd.c, h = qd.h, w = qd.w;
             if (h >= H || w >= W) continue;
-            QuadWork<MODE, GF, 6> qw{gf, zf, sA, sB, gl, goA, goB, lA, oB, oT, gsL, gsT,
+            QuadWork<MODE, GF, 3> qw{gf, zf, sA, sB, gl, goA, goB, lA, oB, oT, gsL, gsT,
                                      a.wT0 + wplane * HW, kT0, kL0, aT0, aL0, G0};
             float ga[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f}, V[4], glr[4], gtvl[4];
-            if (HAS_A) ld4(gA.lrc(r + 6, cq), ga);
-            if (HAS_R) ld4(gB.lrc(r + 6, cq), gb);
+            if (HAS_A) ld4(gA.lrc(r + 3, cq), ga);
+            if (HAS_R) ld4(gB.lrc(r + 3, cq), gb);
             qw.run(r, cq, ga, gb, stF, gsF, ACC_PTR(accF, i, 32), V, glr, gtvl);
             // gradient coming back through the coarse branch (VJP of P is P^T: 0.25 * replicate), inline per coarse pixel
-            const int rc = (r >> 1) + 1, cc = (cq >> 1) + 4, hc = h >> 1, wc = (w >> 1);
+            const int rc = (r >> 1) + 1, cc = (cq >> 1) + 2, hc = h >> 1, wc = (w >> 1);
             float gz0 = S_adj_elem(gsT1.lrc(rc, cc), GC::P, kT1, hc, wc, gc.H, gc.W);
             float gz1 = S_adj_elem(gsT1.lrc(rc, cc + 1), GC::P, kT1, hc, wc + 1, gc.H, gc.W);
             if (HAS_A) {
@@ -490,7 +455,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
                 gz1 += S_adj_elem(gsL1.lrc(rc, cc + 1), GC::P, kL1, hc, wc + 1, gc.H, gc.W);
             }
             float zq[4];
-            ld4(zf.lrc(r + 6, cq), zq);
+            ld4(zf.lrc(r + 3, cq), zq);
             // forward A(z) where the stage needs it (coarse forward term inline, as in the forward kernel)
             float Az[4] = {0.f, 0.f, 0.f, 0.f};
             if (MODE == BWD_X3 || MODE == BWD_X1) {
@@ -563,8 +528,8 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
     {
         float* gwF[2] = {a.gwL0 + wplane * HW, a.gwT0 + wplane * HW};
         EPI_LOOP(i, NQF, 0) {
-            QUAD_ITEM(GF, 0, i, r, cq);
-            const int h = gf.h0 + r, w = gf.gw(cq);
+            const Quad qd = tile_quad_of(gf, i);
+            const int h = qd.h, w = qd.w;
             if (h >= H || w >= W) continue;
             const float* acc = ACC_PTR(accF, i, 32);
 #pragma unroll
@@ -587,8 +552,8 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
         }
         float* gwC[2] = {a.gwL1 + wplane * HWc, a.gwT1 + wplane * HWc};
         EPI_LOOP(i, NQC, NQF) {
-            QUAD_ITEM(GC, 0, i, r, cq);
-            const int h = gc.h0 + r, w = gc.gw(cq);
+            const Quad qd = tile_quad_of(gc, i);
+            const int h = qd.h, w = qd.w;
             if (h >= gc.H || w >= gc.W) continue;
             const float* acc = ACC_PTR(accC, i, 32);
 #pragma unroll

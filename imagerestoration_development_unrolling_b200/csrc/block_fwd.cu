@@ -31,14 +31,15 @@ struct BlockFwdArgs {
     float* out2;  // X2: r1
 };
 
-// shared-memory layout (floats) of one forward stage
+// shared-memory layout (floats) of one forward stage; 4 guard floats on either side (quad 0 / NQ-1 read the scalar
+// left / right of their row, which for the first / last plane row lies just outside the plane)
 template <int MODE, int TH, int TW, int NT>
 struct FwdLayout {
     using GF = Geo<TH, TW, NT>;
     using GC = Geo<TH / 2, TW / 2, NT>;
     static constexpr bool GLR = MODE != MODE_BA, THR = MODE == MODE_X2;
-    static constexpr int zf = 0;
-    static constexpr int sA = zf + GF::floats(6);
+    static constexpr int zf = 4;
+    static constexpr int sA = zf + GF::floats(3);
     static constexpr int sB = sA + (GLR ? GF::floats(2) : 0);
     static constexpr int lA = sB + GF::floats(2);
     static constexpr int oB = lA + (GLR ? GF::floats(1) : 0);
@@ -49,19 +50,23 @@ struct FwdLayout {
     static constexpr int lA1 = sB1 + GC::floats(2);
     static constexpr int oB1 = lA1 + (GLR ? GC::floats(1) : 0);
     static constexpr int oT1 = oB1 + GC::floats(1);
+    // weights: GLR raw (halo 1); GTV as symmetric coefficient planes, or raw (halo 2) where the threshold needs them
     static constexpr int wL0 = oT1 + (THR ? GC::floats(1) : 0);
     static constexpr int cR0 = wL0 + (GLR ? 4 * GF::floats(1) : 0);
-    static constexpr int cD0 = cR0 + GF::floats(2);
-    static constexpr int wT0 = cD0 + GF::floats(2);
+    static constexpr int cD0 = cR0 + (THR ? 0 : GF::floats(2));
+    static constexpr int wT0 = cD0 + (THR ? 0 : GF::floats(2));
     static constexpr int wL1 = wT0 + (THR ? 4 * GF::floats(2) : 0);
     static constexpr int cR1 = wL1 + (GLR ? 4 * GC::floats(1) : 0);
-    static constexpr int cD1 = cR1 + GC::floats(2);
-    static constexpr int wT1 = cD1 + GC::floats(2);
-    static constexpr int total = wT1 + (THR ? 4 * GC::floats(2) : 0);
+    static constexpr int cD1 = cR1 + (THR ? 0 : GC::floats(2));
+    static constexpr int wT1 = cD1 + (THR ? 0 : GC::floats(2));
+    static constexpr int total = wT1 + (THR ? 4 * GC::floats(2) : 0) + 4;
 };
 
+// resident CTAs per SM the shared-memory footprint allows (the register budget follows it)
+constexpr int fwd_min_blocks(int mode) { return mode == MODE_BA ? 4 : 2; }
+
 template <int MODE, int TH, int TW, int NT>
-__global__ void __launch_bounds__(NT) k_block_stage(BlockFwdArgs a) {
+__global__ void __launch_bounds__(NT, fwd_min_blocks(MODE)) k_block_stage(BlockFwdArgs a) {
     GLR_SMEM_DECL(smem);
     using LY = FwdLayout<MODE, TH, TW, NT>;
     using GF = typename LY::GF;
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(NT) k_block_stage(BlockFwdArgs a) {
     GC gc; gc.H = H / 2; gc.W = W / 2; gc.h0 = gf.h0 / 2; gc.w0 = gf.w0 / 2;
     const size_t HW = (size_t)H * W, HWc = HW / 4;
 
-    auto zf = plane_at<GF, 6>(smem, LY::zf);
+    auto zf = plane_at<GF, 3>(smem, LY::zf);
     auto sA = plane_at<GF, 2>(smem, LY::sA);
     auto sB = plane_at<GF, 2>(smem, LY::sB);
     auto lA = plane_at<GF, 1>(smem, LY::lA);
@@ -112,11 +117,12 @@ __global__ void __launch_bounds__(NT) k_block_stage(BlockFwdArgs a) {
 
     // ---- weights of this graph (shared by its F channels)
     const size_t wplane = (size_t)plane * 4;
-    load_gtv_coeffs(gf, cR0, cD0, a.wT0 + wplane * HW);
-    load_gtv_coeffs(gc, cR1, cD1, a.wT1 + wplane * HWc);
     if (THR) {
         load_weights(gf, wT0, a.wT0 + wplane * HW);
         load_weights(gc, wT1, a.wT1 + wplane * HWc);
+    } else {
+        load_gtv_coeffs(gf, cR0, cD0, a.wT0 + wplane * HW);
+        load_gtv_coeffs(gc, cR1, cD1, a.wT1 + wplane * HWc);
     }
     if (GLR) {
         load_weights(gf, wL0, a.wL0 + wplane * HW);
@@ -132,32 +138,42 @@ __global__ void __launch_bounds__(NT) k_block_stage(BlockFwdArgs a) {
         if (GLR) { kL0 = glr_load_taps(a.p.glr0.stats, c); kL1 = glr_load_taps(a.p.glr1.stats, c); }
 
         __syncthreads();  // previous channel's epilogue is done with the planes
-        load_plane<true>(gf, zf, a.z + off);
+        // phase 0: stage input on the tile (+) 3 and its 2x2 mean on the coarse tile (+) 3, one pass over global memory
+        load_fine_and_pooled<true>(gf, gc, zf, pz, a.z + off, (const float*)nullptr, [](float v, float) { return v; });
         __syncthreads();
-        // phase 1: S on the fine grid, pooling
-        stage_S<GLR>(gf, GLR ? sA : sB, GLR ? kL0 : kT0, sB, kT0, zf);
-        stage_pool(gc, pz, zf);
+        // phase 1: S at both resolutions
+        TILE_LOOP_NT(NT, i, GF::items(2)) {
+            const Quad q = quad_of<GF, 2>(gf, i);
+            q_S<GLR>(gf, q, GLR ? sA : sB, GLR ? kL0 : kT0, sB, kT0, zf);
+        }
+        TILE_LOOP_NT(NT, i, GC::items(2)) {
+            const Quad q = quad_of<GC, 2>(gc, i);
+            q_S<GLR>(gc, q, GLR ? sA1 : sB1, GLR ? kL1 : kT1, sB1, kT1, pz);
+        }
         __syncthreads();
-        // phase 2: fine L / GTV cores, coarse S
-        if (GLR) stage_L(gf, lA, sA, wL0);
-        stage_gtv_lin(gf, oB, sB, cR0, cD0);
-        if (THR) stage_gtv_thr(gf, oT, sB, wT0, G0);
-        stage_S<GLR>(gc, GLR ? sA1 : sB1, GLR ? kL1 : kT1, sB1, kT1, pz);
+        // phase 2: L and the GTV cores at both resolutions
+        TILE_LOOP_NT(NT, i, GF::items(1)) {
+            const Quad q = quad_of<GF, 1>(gf, i);
+            if (GLR) q_L(gf, q, lA, sA, wL0);
+            if (THR) q_gtv_raw<true, true>(gf, q, oB, oT, sB, wT0, G0);
+            else q_gtv_lin(gf, q, oB, sB, cR0, cD0);
+        }
+        TILE_LOOP_NT(NT, i, GC::items(1)) {
+            const Quad q = quad_of<GC, 1>(gc, i);
+            if (GLR) q_L(gc, q, lA1, sA1, wL1);
+            if (THR) q_gtv_raw<true, true>(gc, q, oB1, oT1, sB1, wT1, G1);
+            else q_gtv_lin(gc, q, oB1, sB1, cR1, cD1);
+        }
         __syncthreads();
-        // phase 3: coarse cores
-        if (GLR) stage_L(gc, lA1, sA1, wL1);
-        stage_gtv_lin(gc, oB1, sB1, cR1, cD1);
-        if (THR) stage_gtv_thr(gc, oT1, sB1, wT1, G1);
-        __syncthreads();
-        // phase 4: fine St (+ the two coarse St values under each quad) and the stage epilogue
-        TILE_LOOP_NT(NT, i, GF::items(0)) {
-            QUAD_ITEM(GF, 0, i, r, cq);
-            const int h = gf.h0 + r, w = gf.gw(cq);
+        // phase 3: fine St (+ the two coarse St values under each quad) and the stage epilogue
+        TILE_LOOP_NT(NT, i, GF::TR * (GF::NQ - 2)) {
+            const Quad q = tile_quad_of(gf, i);
+            const int r = q.r, cq = q.c, h = q.h, w = q.w;
             if (h >= H || w >= W) continue;
             float zq[4], Az[4], rT[4];
-            ld4(zf.lrc(r + 6, cq), zq);
+            ld4(zf.lrc(r + 3, cq), zq);
             St_quad<GF::P>(oB.lrc(r + 1, cq), kT0, Az);
-            const int rc = (r >> 1) + 1, cc = (cq >> 1) + 4;   // coarse row (halo-1 planes) / column under this quad
+            const int rc = (r >> 1) + 1, cc = (cq >> 1) + 2;   // coarse row (halo-1 planes) / column under this quad
             float tc0 = aT1 * St_elem(oB1.lrc(rc, cc), GC::P, kT1), tc1 = aT1 * St_elem(oB1.lrc(rc, cc + 1), GC::P, kT1);
             if (GLR) {
                 float gl_[4];
@@ -293,7 +309,7 @@ static int launch_stage(const BlockFwdArgs& a, void* stream) {
     const long tiles = (long)((s.W + GLR_TW - 1) / GLR_TW) * ((s.H + GLR_TH - 1) / GLR_TH);
     const long blocks = tiles * s.B * s.G;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
-    constexpr int NT = MODE == MODE_X2 ? 512 : 256;   // X2 holds both cores' planes: 1 CTA/SM, so give it more warps
+    constexpr int NT = 256;
     constexpr size_t smem = (size_t)FwdLayout<MODE, GLR_TH, GLR_TW, NT>::total * sizeof(float);
     static_assert(smem <= 227 * 1024, "forward tile does not fit shared memory");
 #ifndef GLRGTV_EMU
