@@ -190,6 +190,7 @@ def main():
     import torch.distributed as dist
     from imagerestoration_development_unrolling_b200 import _lib as L
     from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
+    from imagerestoration_development_unrolling_b200 import shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -219,9 +220,8 @@ def main():
     def step(inputs):
         outs = [blk(x) for blk, x in zip(blocks, inputs)]
         torch.autograd.backward(outs, gs, inputs=list(inputs) + params)
-        if world > 1:                                   # data-parallel training: gradient all-reduce over NVLink
-            torch.cat([p.grad.reshape(-1) for p in params], out=flat_grad)
-            dist.all_reduce(flat_grad)
+        if world > 1:                                   # data-parallel training: ONE gradient all-reduce over NVLink
+            shard.allreduce_gradients(params, average=False, flat=flat_grad)
         for p in params:
             p.grad = None
         for x in inputs:

@@ -1,0 +1,98 @@
+"""Multi-GPU sharding of the hot path.  The reference has no distributed code at all; this is
+the B200-side addition, one process per GPU over torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+
+* training: batch-sharded data parallelism.  Every op of the block is per-sample, so ranks never exchange
+  activations; `allreduce_gradients` does the ONE collective of a step (flattened parameter gradients).
+* full-resolution inference: row-strip partition of the image with a halo exchange in front of each filter block.
+  One output pixel of a LocalLowpassFilteringBlock depends on inputs at most 25 pixels away at the block's own
+  resolution (3 for bA, 7 for each of the three A(.) applications through the half-resolution branch, 7 for the
+  thresholded right-hand side - SURVEY 8e measured 24-25), so a 26-row halo (even, to keep the 2x2 pooling grid
+  aligned) makes the strip result exact: rows contaminated by the artificial strip border are cropped away, true
+  image borders keep the reference's padding rules because no halo is added there.
+"""
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+BLOCK_HALO_ROWS = 26
+
+
+# ----------------------------------------------------------------------------------------------- training
+def allreduce_gradients(params: Sequence[torch.nn.Parameter], group=None, average: bool = True,
+                        flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Sum (or average) the gradients of `params` across ranks with one all-reduce of a flat buffer and write the
+    result back into each `.grad`.  Parameters without a gradient contribute zeros.  Returns the flat buffer."""
+    params = [p for p in params if p.requires_grad]
+    n = sum(p.numel() for p in params)
+    if flat is None or flat.numel() != n:
+        flat = torch.empty(n, dtype=params[0].dtype, device=params[0].device)
+    o = 0
+    for p in params:
+        seg = flat[o:o + p.numel()]
+        if p.grad is None:
+            seg.zero_()
+        else:
+            seg.copy_(p.grad.reshape(-1))
+        o += p.numel()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, group=group)
+        if average:
+            flat.div_(dist.get_world_size(group))
+    o = 0
+    for p in params:
+        g = flat[o:o + p.numel()].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        o += p.numel()
+    return flat
+
+
+# ----------------------------------------------------------------------------------------------- inference
+def strip_bounds(height: int, world: int, align: int = 2) -> List[Tuple[int, int]]:
+    """[start, stop) rows of every rank: contiguous strips whose boundaries are multiples of `align`
+    (16 at the network input of the 4-scale model: 8x down-sampling times the block's own 2x pooling)."""
+    if height % align:
+        raise ValueError(f"height {height} is not a multiple of the strip alignment {align}")
+    units = height // align
+    base, extra = divmod(units, world)
+    bounds, start = [], 0
+    for r in range(world):
+        n = (base + (1 if r < extra else 0)) * align
+        bounds.append((start, start + n))
+        start += n
+    return bounds
+
+
+def exchange_row_halos(strip: torch.Tensor, halo: int, rank: int, world: int, group=None) -> Tuple[torch.Tensor, int, int]:
+    """Extend a [B,C,h,W] row strip with `halo` rows of each neighbour (none at the true image border).
+    Returns (extended strip, rows added on top, rows added at the bottom)."""
+    if world == 1:
+        return strip, 0, 0
+    if strip.shape[-2] < halo:
+        raise ValueError(f"strip of {strip.shape[-2]} rows is thinner than the {halo}-row halo")
+    up, down = rank - 1, rank + 1
+    ops, top, bot = [], None, None
+    send_top = strip[..., :halo, :].contiguous()
+    send_bot = strip[..., -halo:, :].contiguous()
+    if up >= 0:
+        top = torch.empty_like(send_top)
+        ops += [dist.P2POp(dist.isend, send_top, up, group), dist.P2POp(dist.irecv, top, up, group)]
+    if down < world:
+        bot = torch.empty_like(send_bot)
+        ops += [dist.P2POp(dist.isend, send_bot, down, group), dist.P2POp(dist.irecv, bot, down, group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    parts = ([top] if top is not None else []) + [strip] + ([bot] if bot is not None else [])
+    return torch.cat(parts, dim=-2), (halo if top is not None else 0), (halo if bot is not None else 0)
+
+
+def sharded_block_forward(block: Callable[[torch.Tensor], torch.Tensor], strip: torch.Tensor, rank: int, world: int,
+                          halo: int = BLOCK_HALO_ROWS, group=None) -> torch.Tensor:
+    """Run one filter block on this rank's row strip of a spatially sharded feature map: halo exchange with the two
+    neighbours, the block on the extended strip, crop.  Exact (not approximate) for halo >= 25, see module docstring."""
+    ext, t, b = exchange_row_halos(strip, halo, rank, world, group)
+    out = block(ext)
+    return out[..., t:out.shape[-2] - b, :].contiguous() if (t or b) else out

@@ -1,0 +1,67 @@
+"""Multi-GPU check, launched by hand on a box with >= 2 GPUs:
+
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
+
+(1) spatially sharded inference of a filter block (row strips + NCCL halo exchange) equals the single-GPU result;
+(2) batch-sharded training: all-reduced parameter gradients equal the gradients of the concatenated batch."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M  # noqa: E402
+from imagerestoration_development_unrolling_b200 import shard  # noqa: E402
+from oracle.glr_gtv_oracle import randomize_block_state  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    blk = M.LocalLowpassFilteringBlock(48, 1, 8)
+    blk.load_state_dict(randomize_block_state({k: v.clone() for k, v in blk.state_dict().items()}, seed=1))
+    blk = blk.to(dev)
+    gen = torch.Generator().manual_seed(5)
+
+    # (1) sharded inference on a 1 x 48 x 272 x 480 feature map (a 4K image at 1/8 resolution has 270 x 480)
+    H, W = 16 * 2 * world * 4 + 16, 480
+    x = torch.randn(1, 48, H, W, generator=gen).to(dev)
+    a, b = shard.strip_bounds(H, world, align=2)[rank]
+    with torch.no_grad():
+        full = blk(x)
+        mine = shard.sharded_block_forward(blk, x[:, :, a:b].contiguous(), rank, world)
+    err = float((mine - full[:, :, a:b]).abs().max() / full.abs().max())
+    t = torch.tensor([err], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"sharded inference, {world} strips of a {H}x{W} map: max rel err vs single GPU = {float(t):.2e}")
+    assert float(t) < 1e-6
+
+    # (2) batch-sharded gradients
+    xb = torch.randn(2 * world, 48, 64, 64, generator=gen).to(dev)
+    gb = torch.randn(2 * world, 48, 64, 64, generator=gen).to(dev)
+    params = list(blk.parameters())
+    out = blk(xb)
+    ref = torch.autograd.grad(out, params, gb)
+    out = blk(xb[2 * rank:2 * rank + 2].contiguous())
+    for p, g in zip(params, torch.autograd.grad(out, params, gb[2 * rank:2 * rank + 2].contiguous())):
+        p.grad = g
+    shard.allreduce_gradients(params, average=False)
+    worst = max(float((p.grad - r).norm() / r.norm().clamp_min(1e-20)) for p, r in zip(params, ref) if float(r.abs().max()) > 0)
+    t = torch.tensor([worst], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"batch-sharded training, {world} ranks: worst relative gradient error vs the full batch = {float(t):.2e}")
+    assert float(t) < 1e-4
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""Host-side multi-GPU logic on CPU with the gloo backend, world_size 2 and 3:
+gradient all-reduce for batch-sharded training and row-strip halo exchange for spatially sharded inference.
+The 'block' run on each strip is the CPU oracle, so this also pins the 26-row halo as sufficient for exactness."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import glr_gtv_oracle as O
+from imagerestoration_development_unrolling_b200 import shard
+from tests.util import random_block_state
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _init(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+
+
+def _grad_worker(rank, world, port, q):
+    _init(rank, world, port)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2))]
+    params[0].grad = torch.full((3, 4), float(rank + 1))
+    params[1].grad = torch.arange(5.0) * (rank + 1)
+    # params[2] has no gradient on any rank: must come back as zeros
+    shard.allreduce_gradients(params, average=False)
+    q.put((rank, [p.grad.numpy().copy() for p in params]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_allreduce_gradients(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in range(world))
+    [p.join(60) for p in procs]
+    tot = sum(range(1, world + 1))
+    for r in range(world):
+        g = [torch.from_numpy(t) for t in res[r]]
+        assert torch.equal(g[0], torch.full((3, 4), float(tot)))
+        assert torch.equal(g[1], torch.arange(5.0) * tot)
+        assert torch.equal(g[2], torch.zeros(2, 2))
+
+
+def test_strip_bounds():
+    assert shard.strip_bounds(2160, 8, align=16) == [(0, 272), (272, 544), (544, 816), (816, 1088), (1088, 1360),
+                                                     (1360, 1632), (1632, 1904), (1904, 2160)]
+    assert shard.strip_bounds(64, 3, align=2) == [(0, 22), (22, 44), (44, 64)]
+    with pytest.raises(ValueError):
+        shard.strip_bounds(30, 2, align=4)
+
+
+def _strip_worker(rank, world, port, q, sd, x, bounds):
+    _init(rank, world, port)
+    a, b = bounds[rank]
+    strip = x[:, :, a:b].contiguous()
+    block = lambda t: O.lowpass_block_forward(sd, t)
+    out = shard.sharded_block_forward(block, strip, rank, world)
+    q.put((rank, out.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_block_equals_full_image(world):
+    dim, G, H, W = 12, 2, 96, 24
+    sd = {k: v.double() for k, v in random_block_state(dim, G, seed=9).items()}
+    x = torch.randn(1, dim, H, W, generator=torch.Generator().manual_seed(4), dtype=torch.float64)
+    full = O.lowpass_block_forward(sd, x)
+    bounds = shard.strip_bounds(H, world, align=2)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, q, sd, x, bounds)) for r in range(world)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=300) for _ in range(world))
+    [p.join(60) for p in procs]
+    got = torch.cat([torch.from_numpy(res[r]) for r in range(world)], dim=2)
+    assert got.shape == full.shape
+    assert float((got - full).abs().max()) < 1e-12      # exact: the 26-row halo covers the block's receptive radius
+
+
+def test_halo_must_cover_the_receptive_radius():
+    """a thin halo changes interior strip rows; the 26-row halo (structural radius 25) does not"""
+    dim, G, H, W = 6, 1, 80, 8
+    sd = {k: v.double() for k, v in random_block_state(dim, G, seed=2).items()}
+    x = torch.randn(1, dim, H, W, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    full = O.lowpass_block_forward(sd, x)
+    errs = {}
+    for halo in (8, 26):
+        out = O.lowpass_block_forward(sd, x[:, :, :40 + halo])[:, :, :40]
+        errs[halo] = float((out - full[:, :, :40]).abs().max())
+    assert errs[8] > 1e-9 and errs[26] < 1e-14, errs
