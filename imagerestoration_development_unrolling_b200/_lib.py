@@ -90,6 +90,8 @@ _SIGS = {
     "glrgtv_op_Ct_bwd": (C.c_int, [_P(Shape), _P(Window), fp, fp, fp, fp, fp, fp]),
     "glrgtv_soft_threshold_fwd": (C.c_int, [_P(Shape), C.c_int, fp, fp, fp, fp]),
     "glrgtv_soft_threshold_bwd": (C.c_int, [_P(Shape), C.c_int, fp, fp, fp, fp, fp, fp]),
+    "glrgtv_mixture_fwd": (C.c_int, [_P(Shape), fp, fp, fp, fp]),
+    "glrgtv_mixture_bwd": (C.c_int, [_P(Shape), fp, fp, fp, fp, fp, fp]),
     "glrgtv_pool2_fwd": (C.c_int, [_P(Shape), fp, fp, fp]),
     "glrgtv_unpool2_fwd": (C.c_int, [_P(Shape), fp, fp, fp]),
     "glrgtv_block_fwd": (C.c_int, [_P(Shape), _P(BlockParams), fp, fp, fp, fp, _P(BlockSaved), fp]),

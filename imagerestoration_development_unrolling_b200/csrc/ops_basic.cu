@@ -531,6 +531,43 @@ __global__ void k_gather_bwd(glrgtv_shape s, glrgtv_window win, const float* __r
     }
 }
 
+// ================================================================== mixture weighting (V7:1011-1014)
+// out[b,c,p] = sum_g x[b,g,c,p] * score[b,g,p].   plane = (b,c)
+__global__ void k_mixture_fwd(glrgtv_shape s, const float* __restrict__ x, const float* __restrict__ score,
+                              float* __restrict__ out) {
+    const int HW = s.H * s.W, G = s.G, F = s.F;
+    const int b = blockIdx.x / F, c = blockIdx.x % F;
+    const float* xp = x + ((size_t)b * G * F + c) * HW;
+    const float* sp = score + (size_t)b * G * HW;
+    float* op = out + (size_t)blockIdx.x * HW;
+    PIX_LOOP(i, HW) {
+        float acc = 0.f;
+        for (int g = 0; g < G; ++g) acc += xp[(size_t)g * F * HW + i] * sp[g * HW + i];
+        op[i] = acc;
+    }
+}
+// gx[b,g,c,p] = gout[b,c,p] * score[b,g,p];  gscore[b,g,p] = sum_c gout[b,c,p] * x[b,g,c,p].   plane = (b,g)
+__global__ void k_mixture_bwd(glrgtv_shape s, const float* __restrict__ x, const float* __restrict__ score,
+                              const float* __restrict__ gout, float* __restrict__ gx, float* __restrict__ gscore) {
+    const int HW = s.H * s.W, G = s.G, F = s.F;
+    const int b = blockIdx.x / G;
+    const float* xp = x + (size_t)blockIdx.x * F * HW;
+    const float* sp = score + (size_t)blockIdx.x * HW;
+    const float* gp = gout + (size_t)b * F * HW;
+    float* gxp = gx + (size_t)blockIdx.x * F * HW;
+    float* gsp = gscore + (size_t)blockIdx.x * HW;
+    PIX_LOOP(i, HW) {
+        const float sc = sp[i];
+        float acc = 0.f;
+        for (int c = 0; c < F; ++c) {
+            const float gv = gp[c * HW + i];
+            gxp[c * HW + i] = gv * sc;
+            acc += gv * xp[c * HW + i];
+        }
+        gsp[i] = acc;
+    }
+}
+
 // ================================================================== C ABI
 #define PLANES_C(s) ((long)(s)->B * (s)->G * (s)->F)
 #define PLANES_G(s) ((long)(s)->B * (s)->G)
@@ -727,6 +764,20 @@ int glrgtv_gather_neighbors_bwd(const glrgtv_shape* s, const glrgtv_window* win,
     if (!glr_shape_ok(s) || !glr_window_ok(win)) return GLRGTV_ERR_SHAPE;
     GLR_REQUIRE_PTR(g); GLR_REQUIRE_PTR(gx);
     GLR_LAUNCH(k_gather_bwd, glr_grid(PLANES_C(s), HW_(s), GLR_THREADS), GLR_THREADS, 0, stream, *s, *win, g, gx);
+    return GLR_CHECK_LAUNCH();
+}
+
+int glrgtv_mixture_fwd(const glrgtv_shape* s, const float* x, const float* score, float* out, void* stream) {
+    if (!glr_shape_ok(s)) return GLRGTV_ERR_SHAPE;
+    GLR_REQUIRE_PTR(x); GLR_REQUIRE_PTR(score); GLR_REQUIRE_PTR(out);
+    GLR_LAUNCH(k_mixture_fwd, glr_grid((long)s->B * s->F, HW_(s), GLR_THREADS), GLR_THREADS, 0, stream, *s, x, score, out);
+    return GLR_CHECK_LAUNCH();
+}
+int glrgtv_mixture_bwd(const glrgtv_shape* s, const float* x, const float* score, const float* gout, float* gx,
+                       float* gscore, void* stream) {
+    if (!glr_shape_ok(s)) return GLRGTV_ERR_SHAPE;
+    GLR_REQUIRE_PTR(x); GLR_REQUIRE_PTR(score); GLR_REQUIRE_PTR(gout); GLR_REQUIRE_PTR(gx); GLR_REQUIRE_PTR(gscore);
+    GLR_LAUNCH(k_mixture_bwd, glr_grid(PLANES_G(s), HW_(s), GLR_THREADS), GLR_THREADS, 0, stream, *s, x, score, gout, gx, gscore);
     return GLR_CHECK_LAUNCH();
 }
 

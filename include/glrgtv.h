@@ -144,6 +144,12 @@ int glrgtv_soft_threshold_fwd(const glrgtv_shape* s, int n_edges, const float* t
 int glrgtv_soft_threshold_bwd(const glrgtv_shape* s, int n_edges, const float* t, const float* thr,
                               const float* g, float* gt, float* gthr, void* stream);
 
+/* Mixture weighting of the older family (V7:847-858, 1011-1014): out[b,c] = sum_g x[b,g,c] * score[b,g];
+ * x [B,G,F,H,W], score [B,G,H,W] (already soft-maxed over g), out [B,F,H,W].  bwd writes gx and gscore. */
+int glrgtv_mixture_fwd(const glrgtv_shape* s, const float* x, const float* score, float* out, void* stream);
+int glrgtv_mixture_bwd(const glrgtv_shape* s, const float* x, const float* score, const float* gout, float* gx,
+                       float* gscore, void* stream);
+
 /* 2x2 mean pooling P (V1X0:613, 662-665) and its transpose (V1X0:676-679); each is the other's VJP.
  * `s` is always the FINE geometry (H, W even); coarse tensors are [B,G,F,H/2,W/2]. */
 int glrgtv_pool2_fwd(const glrgtv_shape* s, const float* fine, float* coarse, void* stream);

@@ -1,0 +1,90 @@
+"""Older model family (LIB/model_GLR_GTV_deep_v7.py): oracle pinned to the reference on CPU; drop-in module on GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import glr_gtv_oracle as O
+from tests.util import rel
+
+WINDOW = np.array([[0, 0, 1, 0, 0], [0, 1, 1, 1, 0], [1, 1, 0, 1, 1], [0, 1, 1, 1, 0], [0, 0, 1, 0, 0]])
+
+
+def _golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "v7_mixturegtv_g4.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def test_oracle_solver_matches_reference_fp64(golden_dir):
+    g = _golden(golden_dir)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    out = O.mixture_gtv_solver(sd, g["x"], g["feats"], g["dc"], g["score"], window="small5")
+    assert rel(out, g["out"]) < 1e-13
+
+
+def test_state_dict_layout_matches_reference(golden_dir):
+    from imagerestoration_development_unrolling_b200 import model_GLR_GTV_deep_v7 as M
+    g = _golden(golden_dir)
+    ref_keys = [k[3:] for k in g if k.startswith("sd.")]
+    z = lambda v: torch.tensor([[v], [0.0], [0.0], [0.0]])
+    m = M.MixtureGTV(nchannels_in=3, n_graphs=4, n_node_fts=3, n_cnn_fts=8, connection_window=WINDOW, n_cgd_iters=4,
+                     alpha_init=0.5, beta_init=0.1, muy_init=z(0.1), ro_init=z(0.1), gamma_init=z(0.001), device=torch.device("cpu"))
+    assert list(m.state_dict().keys()) == ref_keys
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(g["sd." + k].shape), k
+    assert [tuple(d) for d in m.GTVmodule00.edge_delta.tolist()] == O.window_edges("small5")
+    # default init of the shipped v7 model (V7:1047-1060)
+    full = M.MultiScaleSequenceDenoiser(torch.device("cpu"))
+    blk = full.mixtureGLR_block03
+    assert blk.n_graphs == 24 and blk.GTVmodule00.n_edges == 12
+    assert torch.allclose(blk.ro00, torch.full((24,), 0.1)) and torch.allclose(blk.gamma00, torch.log(torch.full((24,), 0.001)))
+    assert torch.allclose(full.skip_connect_weight03, torch.tensor([0.1, 0.9]))
+
+
+@pytest.mark.gpu
+def test_mixture_gtv_module_matches_reference_golden(golden_dir):
+    """whole MixtureGTV (CNN + graph solver) with the reference's weights, output and gradients (tolerance 1e-4)"""
+    from imagerestoration_development_unrolling_b200 import model_GLR_GTV_deep_v7 as M
+    g = _golden(golden_dir)
+    z = lambda v: torch.tensor([[v], [0.0], [0.0], [0.0]])
+    m = M.MixtureGTV(nchannels_in=3, n_graphs=4, n_node_fts=3, n_cnn_fts=8, connection_window=WINDOW, n_cgd_iters=4,
+                     alpha_init=0.5, beta_init=0.1, muy_init=z(0.1), ro_init=z(0.1), gamma_init=z(0.001), device=torch.device("cpu"))
+    m.load_state_dict({k[3:]: v.float() for k, v in g.items() if k.startswith("sd.")}, strict=True)
+    m = m.cuda()
+    x = g["x"].float().cuda().requires_grad_(True)
+    out = m(x)
+    names = [k for k, _ in m.named_parameters()]
+    grads = torch.autograd.grad(out, [x] + [p for _, p in m.named_parameters()], g["gout"].float().cuda(), allow_unused=True)
+    assert rel(out, g["out"]) < 1e-4
+    assert rel(grads[0], g["gx"]) < 1e-4
+    for k, gr in zip(names, grads[1:]):
+        if "grad." + k in g and float(g["grad." + k].abs().max()) > 0:
+            assert rel(gr, g["grad." + k]) < 3e-4, (k, rel(gr, g["grad." + k]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("window", ["full3", "small5", "full5"])
+def test_family_a_operators_against_oracle(window):
+    """GLRFast / GTVFast of the older family: any window, reflect S, scalar stats, broadcast signal"""
+    from imagerestoration_development_unrolling_b200 import model_GLR_GTV_deep_v7 as M
+    mask = np.array(O.WINDOWS[window])
+    edges = O.window_edges(window)
+    G, Fn, B, H, W = 5, 3, 2, 9, 11
+    dev = torch.device("cuda")
+    glr, gtv = M.GLRFast(3, Fn, G, mask, dev, 1.0), M.GTVFast(3, Fn, G, mask, dev, 1.0)
+    gen = torch.Generator().manual_seed(len(edges))
+    with torch.no_grad():
+        for mod in (glr, gtv):
+            for p in mod.parameters():
+                p.add_((0.3 * torch.randn(p.shape, generator=gen)).to(dev))
+    feat = torch.randn(B, G, Fn, H, W, generator=gen)
+    y = torch.randn(B, 1, 3, H, W, generator=gen)
+    st = lambda mod: tuple(p.detach().double().cpu() for p in mod._stats())
+    w_ref = O.edge_weights(feat.double(), gtv.multiM.detach().double().cpu(), edges)
+    w, deg = gtv.extract_edge_weights(feat.to(dev))
+    assert rel(w, w_ref) < 1e-5 and float((deg - 1).abs().max()) < 1e-5
+    yG = y.double().expand(B, G, 3, H, W)
+    assert rel(gtv.op_C(y.to(dev), w, deg), O.op_C(yG, w_ref, st(gtv), edges, "reflect")) < 1e-5
+    assert rel(gtv(y.to(dev).expand(B, G, 3, H, W).contiguous(), w, deg), O.gtv_forward(yG, w_ref, st(gtv), edges, "reflect")) < 1e-5
+    assert rel(glr(y.to(dev).expand(B, G, 3, H, W).contiguous(), w, deg), O.glr_forward(yG, w_ref, st(glr), edges, "reflect")) < 1e-5
