@@ -165,9 +165,22 @@ class MixtureGTVGLR(nn.Module):
         ps += [self.alphaCGD, self.betaCGD, self.muys00, self.ro00, self.gamma00, self.muys01, self.ro01, self.gamma01]
         return ps
 
+    def _projections(self, patchs):
+        """patchs_features_extraction00 / 01 (V1X0:556-612, 712, 725) as plain GEMMs on the Conv2d weights: a 1x1 conv is
+        W[2C,C] @ x[C,HW]; the 2x2 stride-2 conv is the same after a space-to-depth.  cuBLAS serves these far better than
+        cuDNN's fp32 convolution fallbacks (profiles/r01_summary.md), and the parameters stay the reference's Conv2d's."""
+        b, c, h, w = patchs.shape
+        w00 = self.patchs_features_extraction00[0].weight.reshape(2 * c, c)
+        w01a = self.patchs_features_extraction01[0].weight.reshape(c, 4 * c)
+        w01b = self.patchs_features_extraction01[1].weight.reshape(2 * c, c)
+        bw = lambda m: m.unsqueeze(0).expand(b, -1, -1)      # batched GEMM keeps [B, out, HW] contiguous (no transposes)
+        feat0 = torch.bmm(bw(w00), patchs.reshape(b, c, h * w)).reshape(b, 2 * c, h, w)
+        xs = nn.functional.pixel_unshuffle(patchs, 2).reshape(b, 4 * c, (h // 2) * (w // 2))
+        feat1 = torch.bmm(bw(w01b), torch.bmm(bw(w01a), xs)).reshape(b, 2 * c, h // 2, w // 2)
+        return feat0, feat1
+
     def forward(self, patchs, _skip_weight=None):
-        feat0 = self.patchs_features_extraction00(patchs)
-        feat1 = self.patchs_features_extraction01(patchs)
+        feat0, feat1 = self._projections(patchs)
         params = self._block_params()
         if _skip_weight is not None:
             params = params + [_skip_weight]
