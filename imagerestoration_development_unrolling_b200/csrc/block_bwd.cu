@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
             if (HAS_A) q_Szero<true, true>(gf, q, gl, kL0, aL0, goA, kT0, aT0, gA);
             if (HAS_R) q_Szero<false, true>(gf, q, goB, kT0, 0.f, goB, kT0, aT0, gB);
         }
-        TILE_LOOP_NT(NT, i, GC::items(2)) {
+        TILE_LOOP_REV(NT, i, GC::items(2)) {
             const Quad q = quad_of<GC, 2>(gc, i);
             q_S<HAS_A>(gc, q, HAS_A ? sA1 : sB1, HAS_A ? kL1 : kT1, sB1, kT1, pz);
             if (HAS_A) q_Szero<true, true>(gc, q, gl1, kL1, aL1, goA1, kT1, aT1, gcA);
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
                 q_gtv_lin(gf, q, gsT, HAS_A ? goA : goB, cR0, cD0);   // the linear core is self-adjoint
             }
         }
-        TILE_LOOP_NT(NT, i, GC::items(1)) {
+        TILE_LOOP_REV(NT, i, GC::items(1)) {
             const Quad q = quad_of<GC, 1>(gc, i);
             if (HAS_A) { q_L(gc, q, lA1, sA1, wL1); q_L_adj(gc, q, gsL1, gl1, wL1); }
             if (THR) {

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NT, fwd_min_blocks(MODE)) k_block_stage(BlockF
             const Quad q = quad_of<GF, 2>(gf, i);
             q_S<GLR>(gf, q, GLR ? sA : sB, GLR ? kL0 : kT0, sB, kT0, zf);
         }
-        TILE_LOOP_NT(NT, i, GC::items(2)) {
+        TILE_LOOP_REV(NT, i, GC::items(2)) {
             const Quad q = quad_of<GC, 2>(gc, i);
             q_S<GLR>(gc, q, GLR ? sA1 : sB1, GLR ? kL1 : kT1, sB1, kT1, pz);
         }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(NT, fwd_min_blocks(MODE)) k_block_stage(BlockF
             if (THR) q_gtv_raw<true, true>(gf, q, oB, oT, sB, wT0, G0);
             else q_gtv_lin(gf, q, oB, sB, cR0, cD0);
         }
-        TILE_LOOP_NT(NT, i, GC::items(1)) {
+        TILE_LOOP_REV(NT, i, GC::items(1)) {
             const Quad q = quad_of<GC, 1>(gc, i);
             if (GLR) q_L(gc, q, lA1, sA1, wL1);
             if (THR) q_gtv_raw<true, true>(gc, q, oB1, oT1, sB1, wT1, G1);

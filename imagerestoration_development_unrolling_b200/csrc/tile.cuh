@@ -37,6 +37,14 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #define TILE_LOOP_NT(NT, i, n) \
     _Pragma("unroll") for (int k_##i = 0, i = threadIdx.x; k_##i < ((n) + (NT)-1) / (NT); ++k_##i, i += (NT)) if (i < (n))
 #endif
+// same loop with the items dealt out from the LAST thread downwards: a phase that runs a fine loop and then a
+// coarse loop gives the extra coarse items to the threads the fine loop left with one item less
+#ifdef GLRGTV_EMU
+#define TILE_LOOP_REV(NT, i, n) for (int i = 0; i < (n); ++i)
+#else
+#define TILE_LOOP_REV(NT, i, n) \
+    _Pragma("unroll") for (int k_##i = 0, i = (NT)-1 - (int)threadIdx.x; k_##i < ((n) + (NT)-1) / (NT); ++k_##i, i += (NT)) if (i < (n))
+#endif
 #define COL0 4  // local column of the tile's first pixel
 
 // geometry of one resolution of a tile: image size, tile origin (global), tile size

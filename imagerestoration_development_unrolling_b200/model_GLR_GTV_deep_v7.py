@@ -230,31 +230,39 @@ class MixtureGTV(nn.Module):
     def soft_threshold(self, delta, gamma):
         return ops.soft_threshold(delta, gamma)
 
+    def unrolled_solve(self, y, wT, wL, schedule=(2, 2)):
+        """The unrolled split-Bregman solver on a signal y [B,1 or G,c,H,W] for given edge weights.
+        `schedule` lists the momentum iterations of each inner solve; between two solves comes one soft-threshold with
+        the dual update.  (2, 2) is V7:964-1000, (2, 4) is v1:627-668, (2, 2, 2) is v0:644-682; alphaCGD / betaCGD need
+        sum(schedule) rows.  Each solve restarts from its right-hand side, its first iteration has no momentum term."""
+        T, bc = self.GTVmodule00, (lambda v: v[None, :, None, None, None])
+        a, be = self.alphaCGD[:, None, :, None, None, None], self.betaCGD[:, None, :, None, None, None]
+        A = lambda z: self.apply_lightweight_transformer(z, [wT], [wL])
+        if sum(schedule) > self.alphaCGD.shape[0]:
+            raise ValueError(f"schedule {schedule} needs {sum(schedule)} rows of alphaCGD, have {self.alphaCGD.shape[0]}")
+        y = T._over_graphs(y, wT[0])
+        eps, bias, k, out = T.op_C(y, *wT), None, 0, None
+        for n_solve, n_it in enumerate(schedule):
+            if n_solve > 0:                                   # threshold + dual update (V7:982-986)
+                t = T.op_C(out, *wT)
+                eps = self.soft_threshold(t if bias is None else t + bias, torch.exp(self.gamma00))
+                bias = (t - eps) if bias is None else bias + (t - eps)
+            rhs = T.op_C_transpose(eps if bias is None else eps - bias, *wT) * bc(self.ro00) + y
+            out, upd = rhs, None
+            for _ in range(n_it):
+                r = rhs - A(out)
+                upd = r if upd is None else r + be[k] * upd
+                out = out + a[k] * upd
+                k += 1
+        return out
+
     def forward(self, patchs):
         feats = self.patchs_features_extraction(patchs)[0]
         b, _, h, w = feats.shape
         gfeat = feats[:, :-12].reshape(b, self.n_graphs, self.n_node_fts, h, w)
         wT, wL = self.GTVmodule00.extract_edge_weights(gfeat), self.GLRmodule00.extract_edge_weights(gfeat)
         dc_term = self.dc_estimator(feats[:, -12:])
-        y = (patchs - dc_term)[:, None]
-        T, bc = self.GTVmodule00, (lambda v: v[None, :, None, None, None])
-        a, be = self.alphaCGD[:, None, :, None, None, None], self.betaCGD[:, None, :, None, None, None]
-        A = lambda z: self.apply_lightweight_transformer(z, [wT], [wL])
-
-        def solve(rhs, k):          # two momentum iterations from `rhs` with alpha/beta rows k, k+1 (V7:973-980)
-            upd = rhs - A(rhs)
-            out = rhs + a[k] * upd
-            upd = (rhs - A(out)) + be[k + 1] * upd
-            return out + a[k + 1] * upd
-
-        eps = T.op_C(y, *wT)
-        rhs = T.op_C_transpose(eps, *wT) * bc(self.ro00) + y
-        out = solve(rhs, 0)
-        t = T.op_C(out, *wT)                                  # bias == 0 before the first threshold
-        eps = self.soft_threshold(t, torch.exp(self.gamma00))
-        bias = t - eps
-        rhs = T.op_C_transpose(eps - bias, *wT) * bc(self.ro00) + y
-        out = solve(rhs, 2)
+        out = self.unrolled_solve((patchs - dc_term)[:, None], wT, wL, schedule=(2, 2))
         score = self.combination_weight(feats[:, :-12])
         return mixture(out.contiguous(), score) + dc_term
 

@@ -407,12 +407,41 @@ def randomize_block_state(sd: Dict[str, torch.Tensor], seed: int, prefix: str = 
 # older family ("family A"): MixtureGTV of LIB/model_GLR_GTV_deep_v7.py:936-1016
 # ----------------------------------------------------------------------------
 
+def unrolled_admm_solve(sd: Dict[str, torch.Tensor], y: torch.Tensor, wT: torch.Tensor, wL: torch.Tensor, edges,
+                        schedule=(2, 2), prefix: str = "") -> torch.Tensor:
+    """Loop-generalised restatement of the older family's solver (v7:964-1000 is schedule (2,2), v1:627-668 is (2,4),
+    v0:644-682 is (2,2,2)): y [B,G,c,H,W]; each entry of `schedule` is one inner solve of that many momentum iterations
+    restarted from its right-hand side; between solves one soft-threshold with the carried dual `bias`."""
+    g = lambda k: sd[prefix + k]
+    T = op_params_from_state(sd, prefix + "GTVmodule00.")
+    Lp = op_params_from_state(sd, prefix + "GLRmodule00.")
+    bc = lambda v: v[None, :, None, None, None]
+    ro, mu, gam = g("ro00"), g("muys00"), g("gamma00").exp()
+    alpha, beta = g("alphaCGD"), g("betaCGD")
+    C = lambda z: op_C(z, wT, T.stats, edges, "reflect")
+    Ct = lambda e: op_Ct(e, wT, T.stats, edges)
+    A = lambda z: (z + bc(mu) * glr_forward(z, wL, Lp.stats, edges, "reflect") + bc(ro) * Ct(C(z)))
+    eps, bias, k, out = C(y), torch.zeros(()), 0, None
+    for n_solve, n_it in enumerate(schedule):
+        if n_solve > 0:
+            t = C(out)
+            eps = soft_threshold(t + bias, gam)
+            bias = bias + (t - eps)
+        rhs = Ct(eps - bias) * bc(ro) + y
+        out, upd = rhs, None
+        for _ in range(n_it):
+            r = rhs - A(out)
+            upd = r if upd is None else r + bc(beta[k]) * upd
+            out = out + bc(alpha[k]) * upd
+            k += 1
+    return out
+
+
 def mixture_gtv_solver(sd: Dict[str, torch.Tensor], patchs: torch.Tensor, feats: torch.Tensor, dc_term: torch.Tensor,
-                       score: torch.Tensor, window="small5", prefix: str = "") -> torch.Tensor:
+                       score: torch.Tensor, window="small5", schedule=(2, 2), prefix: str = "") -> torch.Tensor:
     """The graph part of MixtureGTV.forward given the CNN outputs: feats [B, G*F+12, H, W] (features), dc_term
     [B,3,H,W], score [B,G,H,W] (soft-maxed mixture weights).  Scalar stats parameters, reflect-padded S, the RGB
-    signal broadcast over the G graphs, raw ro/muys, log gamma, one threshold with the dual update (v7:964-1000)."""
-    g = lambda k: sd[prefix + k]
+    signal broadcast over the G graphs, raw ro/muys, log gamma (v7:936-1016)."""
     edges = window_edges(window)
     T = op_params_from_state(sd, prefix + "GTVmodule00.")
     Lp = op_params_from_state(sd, prefix + "GLRmodule00.")
@@ -420,26 +449,6 @@ def mixture_gtv_solver(sd: Dict[str, torch.Tensor], patchs: torch.Tensor, feats:
     B, _, H, W = patchs.shape
     gfeat = feats[:, :-12].reshape(B, G, F, H, W)
     wT, wL = edge_weights(gfeat, T.multiM, edges), edge_weights(gfeat, Lp.multiM, edges)
-    bc = lambda v: v[None, :, None, None, None]
-    ro, mu, gam = g("ro00"), g("muys00"), g("gamma00").exp()
-    alpha, beta = g("alphaCGD"), g("betaCGD")
     y = (patchs - dc_term)[:, None].expand(B, G, 3, H, W)
-
-    C = lambda z: op_C(z, wT, T.stats, edges, "reflect")
-    Ct = lambda e: op_Ct(e, wT, T.stats, edges)
-    A = lambda z: (z + bc(mu) * glr_forward(z, wL, Lp.stats, edges, "reflect") + bc(ro) * Ct(C(z)))
-
-    def solve(rhs, k):
-        upd = rhs - A(rhs)
-        out = rhs + bc(alpha[k]) * upd
-        upd = (rhs - A(out)) + bc(beta[k + 1]) * upd
-        return out + bc(alpha[k + 1]) * upd
-
-    rhs = Ct(C(y)) * bc(ro) + y
-    out = solve(rhs, 0)
-    t = C(out)
-    eps = soft_threshold(t, gam)
-    bias = t - eps
-    rhs = Ct(eps - bias) * bc(ro) + y
-    out = solve(rhs, 2)
+    out = unrolled_admm_solve(sd, y, wT, wL, edges, schedule, prefix)
     return (out * score[:, :, None]).sum(dim=1) + dc_term
