@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libglrgtv.so")
+LIB_PATH = os.environ.get("GLRGTV_LIB") or os.path.join(_PKG, "libglrgtv.so")   # GLRGTV_LIB: an alternative nvcc build
 
 MAX_EDGES = 48
 PAD_CLAMP, PAD_REFLECT = 0, 1

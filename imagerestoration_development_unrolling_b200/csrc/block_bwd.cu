@@ -83,7 +83,11 @@ struct BwdLayout {
     static constexpr int cD1 = cR1 + (THR ? 0 : C2);
     static constexpr int wT1 = cD1 + (THR ? 0 : C2);
     static constexpr int red = wT1 + (THR ? 4 * C2 : 0) + 4;
-    static constexpr int total = red + 64;
+    // cp.async staging of the next channel: z, and the one or two tensors the upstream gradients are built from
+    static constexpr int raw_z = red + 64;
+    static constexpr int raw_g0 = raw_z + Raw<GF>::FLOATS;
+    static constexpr int raw_g1 = raw_g0 + Raw<GF>::FLOATS;
+    static constexpr int total = raw_g1 + (MODE == BWD_X2 ? Raw<GF>::FLOATS : 0);
 };
 
 // per-thread accumulators that live across the channel loop: on the GPU every thread owns at most ONE
@@ -361,28 +365,43 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
     // per-graph sums of this thread: fine [mu0, ro0, gamma0, alpha_k, beta2, skip0, skip1], coarse [mu1, ro1, gamma1]
     float gsF[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gsC[3] = {0.f, 0.f, 0.f};
 
+    float* rz = smem + LY::raw_z;
+    float* rg0 = smem + LY::raw_g0;
+    float* rg1 = smem + LY::raw_g1;
+    // which global tensors feed the upstream gradients of this stage: X3: gout | X2: gout, gx2 | X1: gx1 | BA: gbA
+    const float* src_g0 = (MODE == BWD_X3 || MODE == BWD_X2) ? a.gout : a.gin;
+    const float* src_g1 = MODE == BWD_X2 ? a.gin : nullptr;
+    const size_t plane0 = ((size_t)b * G * F + (size_t)g * F) * HW;
+    auto stage_channel = [&](size_t o) {
+        async_stage_raw(gf, rz, a.z + o);
+        async_stage_raw(gf, rg0, src_g0 + o);
+        if (MODE == BWD_X2) async_stage_raw(gf, rg1, src_g1 + o);
+        cp_async_commit();
+    };
+    stage_channel(plane0);
+
     for (int f = 0; f < F; ++f) {
         const int c = g * F + f;
-        const size_t off = ((size_t)b * G * F + c) * HW;
+        const size_t off = plane0 + (size_t)f * HW;
         const StatsTaps kT0 = glr_load_taps(a.p.gtv0.stats, c), kT1 = glr_load_taps(a.p.gtv1.stats, c);
         const StatsTaps kL0 = glr_load_taps(a.p.glr0.stats, c), kL1 = glr_load_taps(a.p.glr1.stats, c);
 
+        cp_async_wait_all();
         __syncthreads();
         // ---- phase 0: stage input (clamp-extended) and upstream gradients (zero-extended), fine (+)3 and pooled
-        load_fine_and_pooled<true>(gf, gc, zf, pz, a.z + off, (const float*)nullptr, [](float v, float) { return v; });
+        consume_raw<true>(gf, gc, zf, pz, rz, (const float*)nullptr, [](float v, float) { return v; });
         if (MODE == BWD_X3) {
-            load_fine_and_pooled<false>(gf, gc, gA, gcA, a.gout + off, (const float*)nullptr, [=](float go, float) { return -c23 * go; });
+            consume_raw<false>(gf, gc, gA, gcA, rg0, (const float*)nullptr, [=](float go, float) { return -c23 * go; });
         } else if (MODE == BWD_X2) {
-            load_fine_and_pooled<false>(gf, gc, gA, gcA, a.gout + off, a.gin + off,
-                                        [=](float go, float gx2) { return -(be2 * c23 * go + al1 * gx2); });
-            load_fine_and_pooled<false>(gf, gc, gB, gcB, a.gout + off, a.gin + off,
-                                        [=](float go, float gx2) { return c23 * go + (be2 * c23 * go + al1 * gx2); });
+            consume_raw<false>(gf, gc, gA, gcA, rg0, rg1, [=](float go, float gx2) { return -(be2 * c23 * go + al1 * gx2); });
+            consume_raw<false>(gf, gc, gB, gcB, rg0, rg1, [=](float go, float gx2) { return c23 * go + (be2 * c23 * go + al1 * gx2); });
         } else if (MODE == BWD_X1) {
-            load_fine_and_pooled<false>(gf, gc, gA, gcA, a.gin + off, (const float*)nullptr, [=](float gx1, float) { return -al0 * gx1; });
+            consume_raw<false>(gf, gc, gA, gcA, rg0, (const float*)nullptr, [=](float gx1, float) { return -al0 * gx1; });
         } else {
-            load_fine_and_pooled<false>(gf, gc, gB, gcB, a.gin + off, (const float*)nullptr, [](float v, float) { return v; });
+            consume_raw<false>(gf, gc, gB, gcB, rg0, (const float*)nullptr, [](float v, float) { return v; });
         }
         __syncthreads();
+        if (f + 1 < F) stage_channel(off + HW);
         // ---- phase 1: forward S and the St-adjoints of the upstreams, both resolutions
         TILE_LOOP_NT(NT, i, GF::items(2)) {
             const Quad q = quad_of<GF, 2>(gf, i);

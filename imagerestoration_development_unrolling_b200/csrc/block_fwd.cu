@@ -59,11 +59,16 @@ struct FwdLayout {
     static constexpr int cR1 = wL1 + (GLR ? 4 * GC::floats(1) : 0);
     static constexpr int cD1 = cR1 + (THR ? 0 : GC::floats(2));
     static constexpr int wT1 = cD1 + (THR ? 0 : GC::floats(2));
-    static constexpr int total = wT1 + (THR ? 4 * GC::floats(2) : 0) + 4;
+    static constexpr int raw = wT1 + (THR ? 4 * GC::floats(2) : 0) + 4;   // cp.async staging of the next channel
+    static constexpr int total = raw + Raw<GF>::FLOATS;
 };
 
 // resident CTAs per SM the shared-memory footprint allows (the register budget follows it)
+#ifdef GLR_FWD_MINB
+constexpr int fwd_min_blocks(int) { return GLR_FWD_MINB; }
+#else
 constexpr int fwd_min_blocks(int mode) { return mode == MODE_BA ? 4 : 2; }
+#endif
 
 template <int MODE, int TH, int TW, int NT>
 __global__ void __launch_bounds__(NT, fwd_min_blocks(MODE)) k_block_stage(BlockFwdArgs a) {
@@ -130,17 +135,27 @@ __global__ void __launch_bounds__(NT, fwd_min_blocks(MODE)) k_block_stage(BlockF
     }
     const bool vec = (W & 3) == 0;
 
+    float* raw = smem + LY::raw;
+    const size_t plane0 = ((size_t)b * G * F + (size_t)g * F) * HW;
+    async_stage_raw(gf, raw, a.z + plane0);      // channel 0; later channels are staged while their predecessor computes
+    cp_async_commit();
+
     for (int f = 0; f < F; ++f) {
         const int c = g * F + f;
-        const size_t off = ((size_t)b * G * F + c) * HW;
+        const size_t off = plane0 + (size_t)f * HW;
         const StatsTaps kT0 = glr_load_taps(a.p.gtv0.stats, c), kT1 = glr_load_taps(a.p.gtv1.stats, c);
         StatsTaps kL0 = kT0, kL1 = kT1;
         if (GLR) { kL0 = glr_load_taps(a.p.glr0.stats, c); kL1 = glr_load_taps(a.p.glr1.stats, c); }
 
-        __syncthreads();  // previous channel's epilogue is done with the planes
-        // phase 0: stage input on the tile (+) 3 and its 2x2 mean on the coarse tile (+) 3, one pass over global memory
-        load_fine_and_pooled<true>(gf, gc, zf, pz, a.z + off, (const float*)nullptr, [](float v, float) { return v; });
+        cp_async_wait_all();
+        __syncthreads();  // this channel's raw input has landed; the previous channel's epilogue is done with the planes
+        // phase 0: stage input on the tile (+) 3 and its 2x2 mean on the coarse tile (+) 3, from the staged raw buffer
+        consume_raw<true>(gf, gc, zf, pz, raw, (const float*)nullptr, [](float v, float) { return v; });
         __syncthreads();
+        if (f + 1 < F) {
+            async_stage_raw(gf, raw, a.z + off + HW);
+            cp_async_commit();
+        }
         // phase 1: S at both resolutions
         TILE_LOOP_NT(NT, i, GF::items(2)) {
             const Quad q = quad_of<GF, 2>(gf, i);
@@ -298,6 +313,8 @@ __global__ void __launch_bounds__(GLR_THREADS) k_block_weights(glrgtv_shape s, c
 // ---------------------------------------------------------------------------------------------------
 #ifndef GLR_TH
 #define GLR_TH 32
+#endif
+#ifndef GLR_TW
 #define GLR_TW 32
 #endif
 #define GLR_WT_TH 16
@@ -309,7 +326,10 @@ static int launch_stage(const BlockFwdArgs& a, void* stream) {
     const long tiles = (long)((s.W + GLR_TW - 1) / GLR_TW) * ((s.H + GLR_TH - 1) / GLR_TH);
     const long blocks = tiles * s.B * s.G;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
-    constexpr int NT = 256;
+#ifndef GLR_FWD_NT
+#define GLR_FWD_NT 256
+#endif
+    constexpr int NT = GLR_FWD_NT;
     constexpr size_t smem = (size_t)FwdLayout<MODE, GLR_TH, GLR_TW, NT>::total * sizeof(float);
     static_assert(smem <= 227 * 1024, "forward tile does not fit shared memory");
 #ifndef GLRGTV_EMU

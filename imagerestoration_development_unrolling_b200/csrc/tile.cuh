@@ -257,6 +257,95 @@ __device__ __forceinline__ void load_fine_and_pooled(const GF& gf, const GC& gc,
     }
 }
 
+// ------------------------------------------------------------------ asynchronous staging (cp.async)
+// The next channel's input is copied global -> shared with cp.async (LDGSTS, no registers, no stall) into a RAW
+// buffer while the current channel computes: rows [h0-6, h0+TR+6) x columns [w0-8, w0+TC+8), pitch TC+16, holding
+// src[cl(h), cl(w)] (clamped addresses keep every copy in bounds; zero-extension is applied by the consumer).
+template <class GF>
+struct Raw {
+    static constexpr int ROWS = GF::TR + 12, P = GF::TC + 16, NQ = P / 4, FLOATS = ROWS * P;
+};
+#ifdef GLRGTV_EMU
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) { for (int j = 0; j < 4; ++j) dst[j] = src[j]; }
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) { *dst = *src; }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+#endif
+
+// issue (do not wait for) the copy of one channel plane's (+)6 region into `raw`
+template <class GF>
+__device__ __forceinline__ void async_stage_raw(const GF& gf, float* raw, const float* __restrict__ src) {
+    using R = Raw<GF>;
+    const bool vec = (gf.W & 3) == 0;
+    TILE_LOOP_NT(GF::NT, i, R::ROWS * R::NQ) {
+        const int r = i / R::NQ, q = i % R::NQ;
+        const int h = glr_clampi(gf.h0 - 6 + r, 0, gf.H - 1), w = gf.w0 - 8 + 4 * q;
+        const float* row = src + (size_t)h * gf.W;
+        float* dst = raw + r * R::P + 4 * q;
+        if (vec && w >= 0 && w + 3 < gf.W) {
+            cp_async16(dst, row + w);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cp_async4(dst + j, row + glr_clampi(w + j, 0, gf.W - 1));
+        }
+    }
+}
+
+// Consume a staged raw buffer: fine plane (halo 3, clamp- or zero-extended) AND its 2x2 mean (coarse halo 3).
+// One item = a pair of fine rows x one fine quad of the (+)6 region.  FN maps the staged value(s) to the plane
+// value: f(a, b) with a from raw0 and b from raw1 (b = 0 if raw1 is null).
+template <bool CLAMP, class GF, class GC, class FN>
+__device__ __forceinline__ void consume_raw(const GF& gf, const GC& gc, const Plane<GF, 3>& fine, const Plane<GC, 3>& coarse,
+                                            const float* raw0, const float* raw1, FN fn) {
+    using R = Raw<GF>;
+    constexpr int NPAIR = GC::rows(3);               // fine row pairs == coarse rows
+    TILE_LOOP_NT(GF::NT, i, NPAIR * R::NQ) {
+        const int k = i / R::NQ, fq = i % R::NQ;
+        const int h = gf.h0 - 6 + 2 * k, w = gf.w0 - 8 + 4 * fq;       // first fine pixel of the item
+        const int hc = gc.h0 - 3 + k, wc = gc.w0 - 4 + 2 * fq;          // first coarse pixel
+        const int o = 2 * k * R::P + 4 * fq;
+        float a[4], b[4], t0[4], t1[4], u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f}, pooled[2];
+        ld4(raw0 + o, t0); ld4(raw0 + o + R::P, t1);
+        if (raw1) { ld4(raw1 + o, u0); ld4(raw1 + o + R::P, u1); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a[j] = fn(t0[j], u0[j]); b[j] = fn(t1[j], u1[j]); }
+        const bool inside = h >= 0 && h + 1 < gf.H && w >= 0 && w + 3 < gf.W;
+        if (!CLAMP && !inside) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!gf.inside(h, w + j)) a[j] = 0.f;
+                if (!gf.inside(h + 1, w + j)) b[j] = 0.f;
+            }
+        }
+        pooled[0] = 0.25f * (a[0] + a[1] + b[0] + b[1]);
+        pooled[1] = 0.25f * (a[2] + a[3] + b[2] + b[3]);
+        if (CLAMP && !inside) {
+            // the coarse plane is clamp-extended in COARSE coordinates: mean of the 2x2 block of cl(hc, wc)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int y = 2 * glr_clampi(hc, 0, gc.H - 1) - (gf.h0 - 6), x = 2 * glr_clampi(wc + j, 0, gc.W - 1) - (gf.w0 - 8);
+                const float* p0 = raw0 + y * R::P + x;
+                pooled[j] = 0.25f * (fn(p0[0], 0.f) + fn(p0[1], 0.f) + fn(p0[R::P], 0.f) + fn(p0[R::P + 1], 0.f));
+            }
+        }
+        *reinterpret_cast<float2*>(coarse.lrc(k, 2 * fq)) = make_float2(pooled[0], pooled[1]);
+        if (fq >= 1 && fq <= GF::NQ) {
+            const int r0 = 2 * k - 3, c = 4 * fq - 4;
+            if (r0 >= 0 && r0 < GF::rows(3)) st4(fine.lrc(r0, c), a);
+            if (r0 + 1 >= 0 && r0 + 1 < GF::rows(3)) st4(fine.lrc(r0 + 1, c), b);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ forward stages (one quad each)
 __device__ __forceinline__ float s_elem(const float* c, int P, const StatsTaps k) {
     return k.kc * c[0] + k.kr * c[1] + k.kd * c[P] + k.ku * c[-P] + k.kl * c[-1];
