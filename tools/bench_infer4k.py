@@ -1,0 +1,71 @@
+"""BASELINE config 4: 4K (3840x2160) full-image inference of the hot path, spatially sharded.
+
+    python tools/bench_infer4k.py                                   # one GPU, whole image
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 tools/bench_infer4k.py
+
+The four LocalLowpassFilteringBlock of the v13 model run (no_grad) on the feature maps of one 3840x2160 image:
+[1,48,2160,3840], [1,96,1080,1920], [1,192,540,960], [1,384,270,480].  With N ranks every map is cut into N row
+strips (boundaries at even rows) and each block does one 26-row NCCL halo exchange (shard.sharded_block_forward).
+Prints one JSON line: Mpix/s of the network input (8.29 Mpix per image), max over ranks of the CUDA-event time."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M  # noqa: E402
+from imagerestoration_development_unrolling_b200 import shard  # noqa: E402
+
+DIMS, NG, H0, W0 = [48, 96, 192, 384], [8, 16, 16, 32], 2160, 3840
+
+
+def main():
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    blocks = [M.LocalLowpassFilteringBlock(d, 1, g).to(dev) for d, g in zip(DIMS, NG)]
+    strips = []
+    for s, d in enumerate(DIMS):
+        H, W = H0 >> s, W0 >> s
+        a, b = shard.strip_bounds(H, world, align=2)[rank]
+        strips.append(torch.randn(1, d, b - a, W, device=dev, generator=torch.Generator(device=dev).manual_seed(s)))
+
+    def run():
+        with torch.no_grad():
+            return [shard.sharded_block_forward(blk, x, rank, world) for blk, x in zip(blocks, strips)]
+
+    for _ in range(3):
+        run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    if rank == 0:
+        print(json.dumps({"metric": "infer_Mpix_per_s", "value": H0 * W0 / ms / 1e3, "unit": "Mpix/s", "n_gpus": world,
+                          "ms_per_image": ms, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "v13 four filter blocks, forward, feature maps of one 3840x2160 image, row strips + 26-row halo exchange"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
