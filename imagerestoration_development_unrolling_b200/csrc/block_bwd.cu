@@ -21,6 +21,27 @@
 
 enum { BWD_X3 = 0, BWD_X2 = 1, BWD_X1 = 2, BWD_BA = 3 };
 
+// optional per-phase cycle accounting (debug builds only: tools/build_variant.sh x.so -DGLR_PHASE_TIMING)
+#if defined(GLR_PHASE_TIMING) && !defined(GLRGTV_EMU)
+__device__ unsigned long long g_bwd_phase[64];
+#define PHASE_INIT() long long t_prev_ = clock64()
+#define PHASE_MARK(slot)                                                                  \
+    do {                                                                                  \
+        if (threadIdx.x == 0) {                                                           \
+            long long t_ = clock64();                                                     \
+            atomicAdd(&g_bwd_phase[MODE * 8 + (slot)], (unsigned long long)(t_ - t_prev_)); \
+            t_prev_ = t_;                                                                 \
+        }                                                                                 \
+    } while (0)
+extern "C" int glrgtv_debug_bwd_phases(unsigned long long* out, int reset) {
+    if (reset) { unsigned long long z[64] = {0}; return cudaMemcpyToSymbol(g_bwd_phase, z, sizeof(z)) == cudaSuccess ? 0 : -3; }
+    return cudaMemcpyFromSymbol(out, g_bwd_phase, 64 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -3;
+}
+#else
+#define PHASE_INIT() ((void)0)
+#define PHASE_MARK(slot) ((void)0)
+#endif
+
 struct BlockBwdArgs {
     glrgtv_shape s;
     glrgtv_block_params p;
@@ -127,13 +148,27 @@ struct QuadWork {
     Plane<G, RZ> z;
     Plane<G, 2> sA, sB, gl, goA, goB;
     Plane<G, 1> lA, oB, oT, gsL, gsT;
-    const float* wT_global;  // raw GTV weights of this graph at this resolution, [4][H*W]
     StatsTaps kT, kL;
     float aT, aL, Gam;
 
     // r = row within the tile, c = local column of the quad; ga/gb = upstream quads (loaded by the caller)
-    __device__ __forceinline__ void run(int r, int c, const float (&ga)[4], const float (&gb)[4], float* st, float* sums,
-                                        float* acc, float (&V)[4], float (&glr)[4], float (&gtv_lin)[4]) const {
+    // raw GTV weights of one tile quad, [edge][pixel]; they do not depend on the channel
+    __device__ static __forceinline__ void load_we(const G& g, const float* __restrict__ wT_global, int h, int w, float (&we)[4][4]) {
+        const size_t HW = (size_t)g.H * g.W, o = (size_t)h * g.W + w;
+        const bool full = (g.W & 3) == 0 && g.quad_inside(h, w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (full) ld4(wT_global + e * HW + o, we[e]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) we[e][j] = g.inside(h, w + j) ? wT_global[e * HW + o + j] : 0.f;
+            }
+        }
+    }
+
+    __device__ __forceinline__ void run(int r, int c, const float (&ga)[4], const float (&gb)[4], const float (&we)[4][4],
+                                        float* st, float* sums, float* acc, float (&V)[4], float (&glr)[4],
+                                        float (&gtv_lin)[4]) const {
         const int h = g.h0 + r, w = g.gw(c);
         N5 n;
         float gtv_R[4];
@@ -212,17 +247,6 @@ struct QuadWork {
             for (int j = 0; j < 4; ++j) glr[j] = 0.f;
         }
         // ---- edge weights of GTV: gw_e += D phi(t) + D w phi'(t) d  (linear: 2 w D d), D = go[p]-go[n], d = s[p]-s[n]
-        float we[4][4];
-        const size_t HW = (size_t)g.H * g.W, o = (size_t)h * g.W + w;
-        const bool full = (g.W & 3) == 0 && g.quad_inside(h, w);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (full) ld4(wT_global + e * HW + o, we[e]);
-            else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) we[e][j] = g.inside(h, w + j) ? wT_global[e * HW + o + j] : 0.f;
-            }
-        }
         N5 ns;
         ld_n5<P>(sB.lrc(r + 2, c), ns);
         float* accT = acc + 16;
@@ -362,6 +386,22 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc_regs[i] = 0.f;
 #endif
+    // raw GTV weights of this thread's epilogue quad (fine owner or coarse owner): loaded once, reused by every channel
+    float we[4][4];
+#ifndef GLRGTV_EMU
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) we[e][j] = 0.f;
+    EPI_LOOP(i, NQF, 0) {
+        const Quad qd = tile_quad_of(gf, i);
+        if (qd.h < H && qd.w < W) QuadWork<MODE, GF, 3>::load_we(gf, a.wT0 + wplane * HW, qd.h, qd.w, we);
+    }
+    EPI_LOOP(i, NQC, NQF) {
+        const Quad qd = tile_quad_of(gc, i);
+        if (qd.h < gc.H && qd.w < gc.W) QuadWork<MODE, GC, 3>::load_we(gc, a.wT1 + wplane * HWc, qd.h, qd.w, we);
+    }
+#endif
     // per-graph sums of this thread: fine [mu0, ro0, gamma0, alpha_k, beta2, skip0, skip1], coarse [mu1, ro1, gamma1]
     float gsF[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gsC[3] = {0.f, 0.f, 0.f};
 
@@ -379,6 +419,8 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
         cp_async_commit();
     };
     stage_channel(plane0);
+    PHASE_INIT();
+    PHASE_MARK(0);   // prologue: weights, staging of channel 0
 
     for (int f = 0; f < F; ++f) {
         const int c = g * F + f;
@@ -388,6 +430,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
 
         cp_async_wait_all();
         __syncthreads();
+        PHASE_MARK(1);   // wait for the staged input / previous epilogue tail
         // ---- phase 0: stage input (clamp-extended) and upstream gradients (zero-extended), fine (+)3 and pooled
         consume_raw<true>(gf, gc, zf, pz, rz, (const float*)nullptr, [](float v, float) { return v; });
         if (MODE == BWD_X3) {
@@ -401,6 +444,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
             consume_raw<false>(gf, gc, gB, gcB, rg0, (const float*)nullptr, [](float v, float) { return v; });
         }
         __syncthreads();
+        PHASE_MARK(2);   // consume
         if (f + 1 < F) stage_channel(off + HW);
         // ---- phase 1: forward S and the St-adjoints of the upstreams, both resolutions
         TILE_LOOP_NT(NT, i, GF::items(2)) {
@@ -416,6 +460,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
             if (HAS_R) q_Szero<false, true>(gc, q, goB1, kT1, 0.f, goB1, kT1, aT1, gcB);
         }
         __syncthreads();
+        PHASE_MARK(3);   // phase 1
         // ---- phase 2: forward cores and adjoint cores, both resolutions
         TILE_LOOP_NT(NT, i, GF::items(1)) {
             const Quad q = quad_of<GF, 1>(gf, i);
@@ -440,6 +485,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
             }
         }
         __syncthreads();
+        PHASE_MARK(4);   // phase 2
         // ---- phase 3: epilogues.  Threads [0, NQF) own one fine quad each, threads [NQF, NQF+NQC) one coarse quad.
         float stF[10], stC[10];
 #pragma unroll
@@ -448,23 +494,50 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
             const Quad qd = tile_quad_of(gc, i);
             const int r = qd.r, cq = qd.c, h = qd.h, w = qd.w;
             if (h >= gc.H || w >= gc.W) continue;
-            QuadWork<MODE, GC, 3> qw{gc, pz, sA1, sB1, gl1, goA1, goB1, lA1, oB1, oT1, gsL1, gsT1,
-                                     a.wT1 + wplane * HWc, kT1, kL1, aT1, aL1, G1};
+            QuadWork<MODE, GC, 3> qw{gc, pz, sA1, sB1, gl1, goA1, goB1, lA1, oB1, oT1, gsL1, gsT1, kT1, kL1, aT1, aL1, G1};
+#ifdef GLRGTV_EMU
+            QuadWork<MODE, GC, 3>::load_we(gc, a.wT1 + wplane * HWc, h, w, we);
+#endif
             float ga[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f}, V[4], glr[4], gtvl[4];
             if (HAS_A) ld4(gcA.lrc(r + 3, cq), ga);
             if (HAS_R) ld4(gcB.lrc(r + 3, cq), gb);
-            qw.run(r, cq, ga, gb, stC, gsC, ACC_PTR(accC, i, 32), V, glr, gtvl);
+            qw.run(r, cq, ga, gb, we, stC, gsC, ACC_PTR(accC, i, 32), V, glr, gtvl);
         }
         EPI_LOOP(i, NQF, 0) {
             const Quad qd = tile_quad_of(gf, i);
             const int r = qd.r, cq = qd.c, h = qd.h, w = qd.w;
             if (h >= H || w >= W) continue;
-            QuadWork<MODE, GF, 3> qw{gf, zf, sA, sB, gl, goA, goB, lA, oB, oT, gsL, gsT,
-                                     a.wT0 + wplane * HW, kT0, kL0, aT0, aL0, G0};
+            QuadWork<MODE, GF, 3> qw{gf, zf, sA, sB, gl, goA, goB, lA, oB, oT, gsL, gsT, kT0, kL0, aT0, aL0, G0};
+#ifdef GLRGTV_EMU
+            QuadWork<MODE, GF, 3>::load_we(gf, a.wT0 + wplane * HW, h, w, we);
+#endif
+            // pointwise operands from global memory first, so that their latency hides behind the shared-memory work:
+            // q0 gout, q1 gin, q2 r1 / gx2, q3 bB, q4 x
+            const size_t gi = off + (size_t)h * W + w;
+            const bool full = vec && w + 3 < W;
+            float q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f}, q2[4] = {0.f, 0.f, 0.f, 0.f},
+                  q3[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f}, outv[4];
+            if (full) {
+                if (MODE == BWD_X3 || MODE == BWD_X2 || MODE == BWD_BA) ld4(a.gout + gi, q0);
+                if (MODE != BWD_X3) ld4(a.gin + gi, q1);
+                if (MODE == BWD_X3 || MODE == BWD_X2) ld4(a.r1 + gi, q2);
+                if (MODE == BWD_BA) ld4(a.gx2 + gi, q2);
+                if (MODE == BWD_X3) { ld4(a.bB + gi, q3); if (has_skip) ld4(a.x + gi, q4); }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (w + j >= W) continue;
+                    if (MODE == BWD_X3 || MODE == BWD_X2 || MODE == BWD_BA) q0[j] = a.gout[gi + j];
+                    if (MODE != BWD_X3) q1[j] = a.gin[gi + j];
+                    if (MODE == BWD_X3 || MODE == BWD_X2) q2[j] = a.r1[gi + j];
+                    if (MODE == BWD_BA) q2[j] = a.gx2[gi + j];
+                    if (MODE == BWD_X3) { q3[j] = a.bB[gi + j]; if (has_skip) q4[j] = a.x[gi + j]; }
+                }
+            }
             float ga[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f}, V[4], glr[4], gtvl[4];
             if (HAS_A) ld4(gA.lrc(r + 3, cq), ga);
             if (HAS_R) ld4(gB.lrc(r + 3, cq), gb);
-            qw.run(r, cq, ga, gb, stF, gsF, ACC_PTR(accF, i, 32), V, glr, gtvl);
+            qw.run(r, cq, ga, gb, we, stF, gsF, ACC_PTR(accF, i, 32), V, glr, gtvl);
             // gradient coming back through the coarse branch (VJP of P is P^T: 0.25 * replicate), inline per coarse pixel
             const int rc = (r >> 1) + 1, cc = (cq >> 1) + 2, hc = h >> 1, wc = (w >> 1);
             float gz0 = S_adj_elem(gsT1.lrc(rc, cc), GC::P, kT1, hc, wc, gc.H, gc.W);
@@ -483,21 +556,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) Az[j] = zq[j] + aL0 * glr[j] + aT0 * gtvl[j] + 0.25f * (j < 2 ? t0 : t1);
             }
-            const size_t gi = off + (size_t)h * W + w;
-            const bool full = vec && w + 3 < W;
-            float q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f}, q2[4] = {0.f, 0.f, 0.f, 0.f},
-                  q3[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f}, outv[4];
-            // pointwise operands: q0 gout, q1 gin, q2 r1 / gx2, q3 bB, q4 x
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool ok = full || w + j < W;
-                if (!ok) continue;
-                if (MODE == BWD_X3 || MODE == BWD_X2 || MODE == BWD_BA) q0[j] = a.gout[gi + j];
-                if (MODE != BWD_X3) q1[j] = a.gin[gi + j];
-                if (MODE == BWD_X3 || MODE == BWD_X2) q2[j] = a.r1[gi + j];
-                if (MODE == BWD_BA) q2[j] = a.gx2[gi + j];
-                if (MODE == BWD_X3) { q3[j] = a.bB[gi + j]; if (has_skip) q4[j] = a.x[gi + j]; }
-            }
+            // (pointwise operands q0 gout, q1 gin, q2 r1 / gx2, q3 bB, q4 x were loaded at the top of the item)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float Vj = (HAS_A ? ga[j] : 0.f) + V[j] + 0.25f * (j < 2 ? gz0 : gz1);
@@ -529,6 +588,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
         warp_commit<10>(stF, red);
         warp_commit<10>(stC, red + 10);
         __syncthreads();
+        PHASE_MARK(5);   // epilogues + stats commit
         {
             float* dst[4] = {a.gr.gtv0_stats, a.gr.glr0_stats, a.gr.gtv1_stats, a.gr.glr1_stats};
             const int C = G * F;
@@ -541,6 +601,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
         }
         __syncthreads();
         TILE_LOOP_NT(NT, t, 20) red[t] = 0.f;
+        PHASE_MARK(6);   // stats atomics
     }
 
     // ---- edge-weight gradients of this tile: one read-modify-write per stage
@@ -631,7 +692,9 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
 #define GLR_BTH 32
 #define GLR_BTW 32
 #endif
+#ifndef GLR_BWD_THREADS
 #define GLR_BWD_THREADS 384
+#endif
 
 template <int MODE>
 static int launch_bwd_stage(const BlockBwdArgs& a, void* stream) {
