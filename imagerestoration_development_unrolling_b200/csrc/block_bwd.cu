@@ -60,10 +60,10 @@ struct BlockBwdArgs {
 };
 
 // shared-memory layout (floats) of one backward stage (4 guard floats on either side, see FwdLayout)
-template <int MODE, int TH, int TW, int NT>
+template <int MODE, int TH, int TW, int NT, bool GEN>
 struct BwdLayout {
-    using GF = Geo<TH, TW, NT>;
-    using GC = Geo<TH / 2, TW / 2, NT>;
+    using GF = Geo<TH, TW, NT, GEN>;
+    using GC = Geo<TH / 2, TW / 2, NT, GEN>;
     static constexpr bool HAS_A = MODE != BWD_BA, HAS_R = MODE == BWD_X2 || MODE == BWD_BA, THR = MODE == BWD_X2;
     static constexpr int F3 = GF::floats(3), F2 = GF::floats(2), F1 = GF::floats(1);
     static constexpr int C3 = GC::floats(3), C2 = GC::floats(2), C1 = GC::floats(1);
@@ -297,10 +297,10 @@ __device__ __forceinline__ void warp_commit(float* vals, float* sh) {
 #endif
 }
 
-template <int MODE, int TH, int TW, int NT>
+template <int MODE, int TH, int TW, int NT, bool GEN>
 __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
     GLR_SMEM_DECL(smem);
-    using LY = BwdLayout<MODE, TH, TW, NT>;
+    using LY = BwdLayout<MODE, TH, TW, NT, GEN>;
     using GF = typename LY::GF;
     using GC = typename LY::GC;
     constexpr bool HAS_A = LY::HAS_A, HAS_R = LY::HAS_R, THR = LY::THR;
@@ -359,6 +359,12 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
     const bool has_skip = a.p.skip != nullptr;
     const float s0 = has_skip ? a.p.skip[0] : 0.f, s1 = has_skip ? a.p.skip[1] : 1.f;
     const float c23 = al2 * s1;  // gr2 = c23 * gout
+
+    // branch-free borders: the zero-extended planes are zeroed once, outside quads are never written afterwards
+    if (!GEN) {
+        const float z4[4] = {0.f, 0.f, 0.f, 0.f};
+        TILE_LOOP_NT(NT, i, (LY::wL0 - LY::zf) / 4) st4(smem + LY::zf + 4 * i, z4);
+    }
 
     // ---- weights
     const size_t wplane = (size_t)plane * 4;
@@ -696,28 +702,32 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
 #define GLR_BWD_THREADS 384
 #endif
 
-template <int MODE>
-static int launch_bwd_stage(const BlockBwdArgs& a, void* stream) {
+template <int MODE, bool GEN>
+static int launch_bwd_stage_gen(const BlockBwdArgs& a, void* stream) {
     const glrgtv_shape& s = a.s;
     const long tiles = (long)((s.W + GLR_BTW - 1) / GLR_BTW) * ((s.H + GLR_BTH - 1) / GLR_BTH);
     const long blocks = tiles * s.B * s.G;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
-    constexpr size_t smem = (size_t)BwdLayout<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS>::total * sizeof(float);
+    constexpr size_t smem = (size_t)BwdLayout<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS, GEN>::total * sizeof(float);
     static_assert(smem <= 227 * 1024, "backward tile does not fit shared memory");
 #ifndef GLRGTV_EMU
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS>,
+        if (cudaFuncSetAttribute(k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS, GEN>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return glr_record_launch_error();
         configured = true;
     }
 #endif
     GLR_PROF_BEGIN(GLRGTV_SLOT_BWD_X3 + MODE, stream);
-    GLR_LAUNCH((k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS>), dim3((unsigned)blocks), GLR_BWD_THREADS, smem,
-               stream, a);
+    GLR_LAUNCH((k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS, GEN>), dim3((unsigned)blocks), GLR_BWD_THREADS,
+               smem, stream, a);
     GLR_PROF_END(GLRGTV_SLOT_BWD_X3 + MODE, stream);
     return GLR_CHECK_LAUNCH();
+}
+template <int MODE>
+static int launch_bwd_stage(const BlockBwdArgs& a, void* stream) {
+    return (a.s.W % 8 == 0) ? launch_bwd_stage_gen<MODE, false>(a, stream) : launch_bwd_stage_gen<MODE, true>(a, stream);
 }
 
 // tiled edge-weight backward of one resolution (block_weights_bwd.cu)

@@ -33,10 +33,10 @@ struct BlockFwdArgs {
 
 // shared-memory layout (floats) of one forward stage; 4 guard floats on either side (quad 0 / NQ-1 read the scalar
 // left / right of their row, which for the first / last plane row lies just outside the plane)
-template <int MODE, int TH, int TW, int NT>
+template <int MODE, int TH, int TW, int NT, bool GEN>
 struct FwdLayout {
-    using GF = Geo<TH, TW, NT>;
-    using GC = Geo<TH / 2, TW / 2, NT>;
+    using GF = Geo<TH, TW, NT, GEN>;
+    using GC = Geo<TH / 2, TW / 2, NT, GEN>;
     static constexpr bool GLR = MODE != MODE_BA, THR = MODE == MODE_X2;
     static constexpr int zf = 4;
     static constexpr int sA = zf + GF::floats(3);
@@ -70,10 +70,10 @@ constexpr int fwd_min_blocks(int) { return GLR_FWD_MINB; }
 constexpr int fwd_min_blocks(int mode) { return mode == MODE_BA ? 4 : 2; }
 #endif
 
-template <int MODE, int TH, int TW, int NT>
+template <int MODE, int TH, int TW, int NT, bool GEN>
 __global__ void __launch_bounds__(NT, fwd_min_blocks(MODE)) k_block_stage(BlockFwdArgs a) {
     GLR_SMEM_DECL(smem);
-    using LY = FwdLayout<MODE, TH, TW, NT>;
+    using LY = FwdLayout<MODE, TH, TW, NT, GEN>;
     using GF = typename LY::GF;
     using GC = typename LY::GC;
     constexpr bool GLR = LY::GLR, THR = LY::THR;
@@ -119,6 +119,12 @@ __global__ void __launch_bounds__(NT, fwd_min_blocks(MODE)) k_block_stage(BlockF
         if (a.p.skip) { s0 = a.p.skip[0]; s1 = a.p.skip[1]; }
     }
     const bool has_skip = MODE == MODE_X3 && a.p.skip != nullptr;
+
+    // branch-free borders: the zero-extended planes are zeroed once, outside quads are never written afterwards
+    if (!GEN) {
+        const float z4[4] = {0.f, 0.f, 0.f, 0.f};
+        TILE_LOOP_NT(NT, i, (LY::wL0 - LY::zf) / 4) st4(smem + LY::zf + 4 * i, z4);
+    }
 
     // ---- weights of this graph (shared by its F channels)
     const size_t wplane = (size_t)plane * 4;
@@ -320,8 +326,8 @@ __global__ void __launch_bounds__(GLR_THREADS) k_block_weights(glrgtv_shape s, c
 #define GLR_WT_TH 16
 #define GLR_WT_TW 32
 
-template <int MODE>
-static int launch_stage(const BlockFwdArgs& a, void* stream) {
+template <int MODE, bool GEN>
+static int launch_stage_gen(const BlockFwdArgs& a, void* stream) {
     const glrgtv_shape& s = a.s;
     const long tiles = (long)((s.W + GLR_TW - 1) / GLR_TW) * ((s.H + GLR_TH - 1) / GLR_TH);
     const long blocks = tiles * s.B * s.G;
@@ -330,21 +336,26 @@ static int launch_stage(const BlockFwdArgs& a, void* stream) {
 #define GLR_FWD_NT 256
 #endif
     constexpr int NT = GLR_FWD_NT;
-    constexpr size_t smem = (size_t)FwdLayout<MODE, GLR_TH, GLR_TW, NT>::total * sizeof(float);
+    constexpr size_t smem = (size_t)FwdLayout<MODE, GLR_TH, GLR_TW, NT, GEN>::total * sizeof(float);
     static_assert(smem <= 227 * 1024, "forward tile does not fit shared memory");
 #ifndef GLRGTV_EMU
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_block_stage<MODE, GLR_TH, GLR_TW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(k_block_stage<MODE, GLR_TH, GLR_TW, NT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return glr_record_launch_error();
         configured = true;
     }
 #endif
     GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_BA + MODE, stream);
-    GLR_LAUNCH((k_block_stage<MODE, GLR_TH, GLR_TW, NT>), dim3((unsigned)blocks), NT, smem, stream, a);
+    GLR_LAUNCH((k_block_stage<MODE, GLR_TH, GLR_TW, NT, GEN>), dim3((unsigned)blocks), NT, smem, stream, a);
     GLR_PROF_END(GLRGTV_SLOT_FWD_BA + MODE, stream);
     return GLR_CHECK_LAUNCH();
+}
+// W % 8 == 0 (quads never straddle the image border at either resolution) takes the branch-free kernels
+template <int MODE>
+static int launch_stage(const BlockFwdArgs& a, void* stream) {
+    return (a.s.W % 8 == 0) ? launch_stage_gen<MODE, false>(a, stream) : launch_stage_gen<MODE, true>(a, stream);
 }
 
 static int launch_weights(const glrgtv_shape& s, const float* feat, const float* Mt, const float* Ml, float* wt,

@@ -48,9 +48,12 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #define COL0 4  // local column of the tile's first pixel
 
 // geometry of one resolution of a tile: image size, tile origin (global), tile size
-template <int TR_, int TC_, int NT_>
+// GEN_ = true: generic borders (any even W); false: W is a multiple of 4 at this resolution, so every quad lies fully
+// inside or fully outside the image and the stage bodies are branch-free (see "branch-free borders" below)
+template <int TR_, int TC_, int NT_, bool GEN_ = true>
 struct Geo {
     static constexpr int TR = TR_, TC = TC_, P = TC_ + 8, NT = NT_, NQ = P / 4;
+    static constexpr bool GEN = GEN_;
     int H, W, h0, w0;
     static constexpr int rows(int R) { return TR + 2 * R; }
     static constexpr int items(int R) { return rows(R) * NQ; }   // quads of a halo-R plane
@@ -109,7 +112,8 @@ __device__ __forceinline__ void ld_n5(const float* s, N5& n) {
 // one quad of a halo-R plane: local row / column, global coordinates of its first pixel, fast-path flag
 struct Quad {
     int r, c, h, w;
-    bool fast;
+    bool fast;     // all four pixels inside the image
+    bool border;   // fast and touching the image border (its values are replicated outwards in branch-free mode)
 };
 template <class G, int R>
 __device__ __forceinline__ Quad quad_of(const G& g, int i) {
@@ -119,6 +123,7 @@ __device__ __forceinline__ Quad quad_of(const G& g, int i) {
     q.h = g.gh(q.r, R);
     q.w = g.gw(q.c);
     q.fast = g.quad_inside(q.h, q.w);
+    q.border = q.fast && (q.h == 0 || q.h == g.H - 1 || q.w == 0 || q.w + 4 == g.W);
     return q;
 }
 // the quads of the tile itself (halo 0): NQ-2 per row, starting at local column 4
@@ -130,7 +135,32 @@ __device__ __forceinline__ Quad tile_quad_of(const G& g, int i) {
     q.h = g.h0 + q.r;
     q.w = g.gw(q.c);
     q.fast = g.quad_inside(q.h, q.w);
+    q.border = false;
     return q;
+}
+
+// ---- branch-free borders (G::GEN == false).  Outside quads are skipped altogether: zero-extended planes are zeroed
+// once per CTA and never written outside the image; clamp-extended planes get their outside copies from the inside
+// quad next to the border, which stores its edge values outwards (up to R rows, one quad sideways, and the corners).
+template <class G, int R>
+__device__ __forceinline__ void replicate_out(const G& g, const Quad& q, const Plane<G, R>& dst, const float (&v)[4]) {
+    const bool L = q.w == 0 && q.c >= 4, Rt = q.w + 4 == g.W && q.c + 8 <= G::P, U = q.h == 0, D = q.h == g.H - 1;
+    const float lv[4] = {v[0], v[0], v[0], v[0]}, rv[4] = {v[3], v[3], v[3], v[3]};
+    if (L) st4(dst.lrc(q.r, q.c - 4), lv);
+    if (Rt) st4(dst.lrc(q.r, q.c + 4), rv);
+#pragma unroll
+    for (int k = 1; k <= R; ++k) {
+        if (U && q.r - k >= 0) {
+            st4(dst.lrc(q.r - k, q.c), v);
+            if (L) st4(dst.lrc(q.r - k, q.c - 4), lv);
+            if (Rt) st4(dst.lrc(q.r - k, q.c + 4), rv);
+        }
+        if (D && q.r + k < G::rows(R)) {
+            st4(dst.lrc(q.r + k, q.c), v);
+            if (L) st4(dst.lrc(q.r + k, q.c - 4), lv);
+            if (Rt) st4(dst.lrc(q.r + k, q.c + 4), rv);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ loads from global memory
@@ -355,8 +385,9 @@ template <bool TWO, class G, int RD, int RS>
 __device__ __forceinline__ void q_S(const G& g, const Quad& q, const Plane<G, RD>& dA, const StatsTaps kA,
                                     const Plane<G, RD>& dB, const StatsTaps kB, const Plane<G, RS>& src) {
     static_assert(RS >= RD + 1, "halo");
+    if (!G::GEN && !q.fast) return;
     float a[4], b[4];
-    if (q.fast) {
+    if (!G::GEN || q.fast) {
         N5 n;
         ld_n5<G::P>(src.lrc(q.r + RS - RD, q.c), n);
 #pragma unroll
@@ -374,14 +405,19 @@ __device__ __forceinline__ void q_S(const G& g, const Quad& q, const Plane<G, RD
     }
     st4(dA.lrc(q.r, q.c), a);
     if (TWO) st4(dB.lrc(q.r, q.c), b);
+    if (!G::GEN && q.border) {
+        replicate_out(g, q, dA, a);
+        if (TWO) replicate_out(g, q, dB, b);
+    }
 }
 
 // L: s clamp-extended (halo RS) -> dst zero-extended (halo RD): s - sum_e w_e s[n_e]; weights halo RW >= RD
 template <class G, int RD, int RS, int RW>
 __device__ __forceinline__ void q_L(const G& g, const Quad& q, const Plane<G, RD>& dst, const Plane<G, RS>& s,
                                     const WPl<G, RW>& w) {
+    if (!G::GEN && !q.fast) return;
     float v[4];
-    if (q.fast) {
+    if (!G::GEN || q.fast) {
         N5 n;
         ld_n5<G::P>(s.lrc(q.r + RS - RD, q.c), n);
         float w0[4], w1[4], w2[4], w3[4];
@@ -413,8 +449,9 @@ template <class G, int RD, int RS, int RC>
 __device__ __forceinline__ void q_gtv_lin(const G& g, const Quad& q, const Plane<G, RD>& dst, const Plane<G, RS>& s,
                                           const Plane<G, RC>& cR, const Plane<G, RC>& cD) {
     static_assert(RC >= RD + 1 && RS >= RD + 1, "halo");
+    if (!G::GEN && !q.fast) return;
     float v[4];
-    if (q.fast) {
+    if (!G::GEN || q.fast) {
         N5 n;
         ld_n5<G::P>(s.lrc(q.r + RS - RD, q.c), n);
         float cr[4], cd[4], cu[4];
@@ -465,8 +502,9 @@ template <bool LIN, bool THR, class G, int RD, int RS, int RW>
 __device__ __forceinline__ void q_gtv_raw(const G& g, const Quad& q, const Plane<G, RD>& dLin, const Plane<G, RD>& dThr,
                                           const Plane<G, RS>& s, const WPl<G, RW>& w, float Gam) {
     static_assert(RW >= RD + 1 && RS >= RD + 1, "halo");
+    if (!G::GEN && !q.fast) return;
     float vl[4] = {0.f, 0.f, 0.f, 0.f}, vt[4] = {0.f, 0.f, 0.f, 0.f};
-    if (q.fast) {
+    if (!G::GEN || q.fast) {
         N5 n;
         ld_n5<G::P>(s.lrc(q.r + RS - RD, q.c), n);
         QW qw;
@@ -526,8 +564,9 @@ template <bool HAS_Z, bool HAS_C, class G, int RD, int RS>
 __device__ __forceinline__ void q_Szero(const G& g, const Quad& q, const Plane<G, RD>& dZ, const StatsTaps kZ, float sZ,
                                         const Plane<G, RD>& dC, const StatsTaps kC, float sC, const Plane<G, RS>& src) {
     static_assert(RS >= RD + 1, "halo");
+    if (!G::GEN && !q.fast) return;
     float z[4], c[4];
-    if (q.fast) {
+    if (!G::GEN || q.fast) {
         N5 n;
         ld_n5<G::P>(src.lrc(q.r + RS - RD, q.c), n);
 #pragma unroll
@@ -544,6 +583,7 @@ __device__ __forceinline__ void q_Szero(const G& g, const Quad& q, const Plane<G
     }
     if (HAS_Z) st4(dZ.lrc(q.r, q.c), z);
     if (HAS_C) st4(dC.lrc(q.r, q.c), c);
+    if (!G::GEN && HAS_C && q.border) replicate_out(g, q, dC, c);
 }
 
 // VJP of L wrt its input, zero-extended: gs[q] = gl[q] - sum_n w_{n->q}[n] gl[n] - sum_{e: q+d_e outside} w_e[q] gl[q]
@@ -552,9 +592,10 @@ template <class G, int RD, int RS, int RW>
 __device__ __forceinline__ void q_L_adj(const G& g, const Quad& q, const Plane<G, RD>& dst, const Plane<G, RS>& gl,
                                         const WPl<G, RW>& w) {
     static_assert(RS >= RD + 1 && RW >= RD + 1, "halo");
+    if (!G::GEN && !q.fast) return;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     const int h = q.h, x = q.w;
-    if (q.fast) {
+    if (!G::GEN || q.fast) {
         N5 n;
         ld_n5<G::P>(gl.lrc(q.r + RS - RD, q.c), n);
         const int rw = q.r + RW - RD;
@@ -619,8 +660,9 @@ __device__ __forceinline__ float S_adj_elem(const float* c, int P, const StatsTa
 template <bool LIN, bool THR, class G, int RD, int RG, int RS, int RW>
 __device__ __forceinline__ void q_gtv_raw_adj(const G& g, const Quad& q, const Plane<G, RD>& dst, const Plane<G, RG>& goA,
                                               const Plane<G, RG>& goB, const Plane<G, RS>& s, const WPl<G, RW>& w, float Gam) {
+    if (!G::GEN && !q.fast) return;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (q.fast) {
+    if (!G::GEN || q.fast) {
         N5 na, nb, ns;
         if (LIN) ld_n5<G::P>(goA.lrc(q.r + RG - RD, q.c), na);
         if (THR) { ld_n5<G::P>(goB.lrc(q.r + RG - RD, q.c), nb); ld_n5<G::P>(s.lrc(q.r + RS - RD, q.c), ns); }

@@ -9,7 +9,9 @@ from tests.util import (rel, random_block_state, block_structs, alloc_saved, ora
                         grads_to_state_names)
 
 # (dim, ngraphs, B, H, W): partial tiles, multi-tile (tile = 32x32), smallest legal size
-CASES = [(12, 2, 2, 12, 20), (24, 2, 1, 34, 66), (24, 4, 1, 2, 4), (6, 1, 1, 64, 32), (12, 2, 1, 40, 36)]
+# widths that are multiples of 8 take the branch-free kernels, the others the generic ones
+CASES = [(12, 2, 2, 12, 20), (24, 2, 1, 34, 66), (24, 4, 1, 2, 4), (6, 1, 1, 64, 32), (12, 2, 1, 40, 36),
+         (12, 2, 1, 40, 24), (24, 2, 1, 34, 64), (12, 2, 2, 16, 8), (6, 1, 1, 70, 72)]
 
 
 @pytest.mark.parametrize("case", CASES)
