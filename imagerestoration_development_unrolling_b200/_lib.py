@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("GLRGTV_LIB") or os.path.join(_PKG, "libglrgtv.so")   
 
 MAX_EDGES = 48
 PAD_CLAMP, PAD_REFLECT = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _STATUS = {
     0: "GLRGTV_OK", -1: "GLRGTV_ERR_SHAPE", -2: "GLRGTV_ERR_POINTER", -3: "GLRGTV_ERR_CUDA",
@@ -50,7 +50,7 @@ class BlockGrads(C.Structure):
 
 
 class BlockSaved(C.Structure):
-    _fields_ = [(n, fp) for n in ("wT0", "wL0", "wT1", "wL1", "bA", "x1", "bB", "r1", "x2")]
+    _fields_ = [(n, fp) for n in ("wT0", "wL0", "wT1", "wL1", "bA", "x1", "bB", "r1", "x2", "cT0", "cT1")]
 
 
 def make_window(edges) -> Window:
@@ -71,6 +71,7 @@ _SIGS = {
     "glrgtv_check_device": (C.c_int, []),
     "glrgtv_launch_count": (C.c_ulonglong, []),
     "glrgtv_profile_enable": (C.c_int, [C.c_int]),
+    "glrgtv_set_block_path": (C.c_int, [C.c_int]),
     "glrgtv_profile_read": (C.c_int, [_P(C.c_float), _P(C.c_int), C.c_int]),
     "glrgtv_edge_weights_fwd": (C.c_int, [_P(Shape), _P(Window), fp, fp, fp, fp]),
     "glrgtv_edge_weights_bwd": (C.c_int, [_P(Shape), _P(Window), fp, fp, fp, fp, fp, fp, fp, fp]),

@@ -5,6 +5,83 @@
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 alignas(64) static thread_local float emu_smem_storage[64 * 1024];
 thread_local float* emu_smem = emu_smem_storage;
+
+// ---- cooperative fibers: one per CUDA thread of the block being emulated (ucontext, round-robin) ----
+#include <ucontext.h>
+#include <vector>
+thread_local bool emu_fiber_mode = false;
+namespace {
+constexpr size_t kStack = 256 * 1024;
+struct FiberRt {
+    std::vector<ucontext_t> ctx;
+    std::vector<char*> stacks;
+    std::vector<char> done;
+    ucontext_t sched;
+    unsigned n = 0, cur = 0, alive = 0;
+    unsigned bar_count = 0, bar_gen = 0;
+    std::vector<float> buf[2];
+    std::vector<unsigned> cnt, gen;
+    void (*fn)(void*) = nullptr;
+    void* arg = nullptr;
+};
+thread_local FiberRt rt;
+void fiber_yield() { swapcontext(&rt.ctx[rt.cur], &rt.sched); }
+void fiber_main() {
+    rt.fn(rt.arg);
+    rt.done[rt.cur] = 1;
+    swapcontext(&rt.ctx[rt.cur], &rt.sched);
+}
+}  // namespace
+void emu_barrier() {
+    const unsigned g = rt.bar_gen;
+    if (++rt.bar_count >= rt.alive) { rt.bar_count = 0; ++rt.bar_gen; return; }
+    while (rt.bar_gen == g) fiber_yield();
+}
+float emu_shfl(float v, int src_lane) {
+    if (!emu_fiber_mode) return v;
+    const unsigned me = rt.cur, w = me >> 5, base = w << 5;
+    const unsigned wsize = rt.n - base < 32u ? rt.n - base : 32u;
+    const unsigned g = rt.gen[w];
+    rt.buf[g & 1][me] = v;
+    if (++rt.cnt[w] == wsize) { rt.cnt[w] = 0; ++rt.gen[w]; }
+    else while (rt.gen[w] == g) fiber_yield();
+    return rt.buf[g & 1][base + (unsigned)src_lane];
+}
+void emu_run_block(unsigned nthreads, void (*fn)(void*), void* arg) {
+    rt.n = nthreads; rt.alive = nthreads; rt.fn = fn; rt.arg = arg;
+    rt.bar_count = 0; rt.bar_gen = 0;
+    if (rt.ctx.size() < nthreads) {
+        const size_t old = rt.ctx.size();
+        rt.ctx.resize(nthreads);
+        rt.stacks.resize(nthreads, nullptr);
+        for (size_t i = old; i < nthreads; ++i) rt.stacks[i] = (char*)malloc(kStack);
+    }
+    rt.done.assign(nthreads, 0);
+    rt.buf[0].assign(nthreads, 0.f); rt.buf[1].assign(nthreads, 0.f);
+    rt.cnt.assign((nthreads + 31) / 32, 0); rt.gen.assign((nthreads + 31) / 32, 0);
+    for (unsigned i = 0; i < nthreads; ++i) {
+        getcontext(&rt.ctx[i]);
+        rt.ctx[i].uc_stack.ss_sp = rt.stacks[i];
+        rt.ctx[i].uc_stack.ss_size = kStack;
+        rt.ctx[i].uc_link = &rt.sched;
+        makecontext(&rt.ctx[i], fiber_main, 0);
+    }
+    emu_fiber_mode = true;
+    unsigned remaining = nthreads;
+    while (remaining) {
+        for (unsigned i = 0; i < nthreads; ++i) {
+            if (rt.done[i]) continue;
+            rt.cur = i;
+            threadIdx = emu_dim3(i, 0, 0);
+            swapcontext(&rt.sched, &rt.ctx[i]);
+            if (rt.done[i]) {
+                --remaining; --rt.alive;
+                if (rt.bar_count && rt.bar_count >= rt.alive) { rt.bar_count = 0; ++rt.bar_gen; }
+            }
+        }
+    }
+    emu_fiber_mode = false;
+}
 extern "C" {
 int glrgtv_abi_version(void) { return GLRGTV_ABI_VERSION; }
 const char* glrgtv_last_cuda_error(void) { return "emulation build"; }

@@ -193,13 +193,16 @@ struct QuadWork {
         N5 nz;
         ld_n5<P>(z.lrc(r + RZ, c), nz);
         ld_n5<P>(gsT.lrc(r + 1, c), n);
+        const bool edge = h == 0 || h == g.H - 1 || w == 0 || w + 4 >= g.W;   // only border quads collect replicated taps
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float self = 0.f;
-            if (w + j == g.W - 1) self += kT.kr;
-            if (h == g.H - 1) self += kT.kd;
-            if (h == 0) self += kT.ku;
-            if (w + j == 0) self += kT.kl;
+            if (edge) {
+                if (w + j == g.W - 1) self += kT.kr;
+                if (h == g.H - 1) self += kT.kd;
+                if (h == 0) self += kT.ku;
+                if (w + j == 0) self += kT.kl;
+            }
             V[j] = (kT.kc + self) * n.c[j] + kT.kr * n.L(j) + kT.kd * n.u[j] + kT.ku * n.d[j] + kT.kl * n.Rr(j);
             const float gs = n.c[j];
             stats_acc(st, gs, nz.c[j], nz.Rr(j), nz.d[j], nz.u[j], nz.L(j));
@@ -223,10 +226,12 @@ struct QuadWork {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float self = 0.f;
-                if (w + j == g.W - 1) self += kL.kr;
-                if (h == g.H - 1) self += kL.kd;
-                if (h == 0) self += kL.ku;
-                if (w + j == 0) self += kL.kl;
+                if (edge) {
+                    if (w + j == g.W - 1) self += kL.kr;
+                    if (h == g.H - 1) self += kL.kd;
+                    if (h == 0) self += kL.ku;
+                    if (w + j == 0) self += kL.kl;
+                }
                 V[j] += (kL.kc + self) * n.c[j] + kL.kr * n.L(j) + kL.kd * n.u[j] + kL.ku * n.d[j] + kL.kl * n.Rr(j);
                 const float gs = n.c[j];
                 stats_acc(st + 5, gs, nz.c[j], nz.Rr(j), nz.d[j], nz.u[j], nz.L(j));
@@ -520,7 +525,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
             // pointwise operands from global memory first, so that their latency hides behind the shared-memory work:
             // q0 gout, q1 gin, q2 r1 / gx2, q3 bB, q4 x
             const size_t gi = off + (size_t)h * W + w;
-            const bool full = vec && w + 3 < W;
+            const bool full = !GEN || (vec && w + 3 < W);
             float q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f}, q2[4] = {0.f, 0.f, 0.f, 0.f},
                   q3[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f}, outv[4];
             if (full) {
@@ -625,7 +630,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
                 for (int e = 0; e < 4; ++e) {
                     float* q = gwF[m] + (size_t)e * HW + (size_t)h * W + w;
                     float v[4] = {acc[m * 16 + e * 4 + 0], acc[m * 16 + e * 4 + 1], acc[m * 16 + e * 4 + 2], acc[m * 16 + e * 4 + 3]};
-                    if (vec && w + 3 < W) {
+                    if (!GEN || (vec && w + 3 < W)) {
                         if (!a.gw_assign) { float o[4]; ld4(q, o); v[0] += o[0]; v[1] += o[1]; v[2] += o[2]; v[3] += o[3]; }
                         st4(q, v);
                     } else {
@@ -649,7 +654,7 @@ __global__ void __launch_bounds__(NT) k_block_bwd_stage(BlockBwdArgs a) {
                 for (int e = 0; e < 4; ++e) {
                     float* q = gwC[m] + (size_t)e * HWc + (size_t)h * gc.W + w;
                     float v[4] = {acc[m * 16 + e * 4 + 0], acc[m * 16 + e * 4 + 1], acc[m * 16 + e * 4 + 2], acc[m * 16 + e * 4 + 3]};
-                    if (vecc && w + 3 < gc.W) {
+                    if (!GEN || (vecc && w + 3 < gc.W)) {
                         if (!a.gw_assign) { float o[4]; ld4(q, o); v[0] += o[0]; v[1] += o[1]; v[2] += o[2]; v[3] += o[3]; }
                         st4(q, v);
                     } else {

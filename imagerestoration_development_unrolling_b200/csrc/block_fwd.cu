@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NT, fwd_min_blocks(MODE)) k_block_stage(BlockF
                 for (int j = 0; j < 4; ++j) rT[j] = aT0 * rT[j] + 0.25f * (j < 2 ? t0 : t1);
             }
             const size_t gi = off + (size_t)h * W + w;
-            const bool full = vec && w + 3 < W;
+            const bool full = !GEN || (vec && w + 3 < W);
             float o0[4], o1[4], o2[4], in0[4], in1[4], in2[4];
             // pointwise operands
             if (MODE == MODE_X2 || MODE == MODE_X3) {
@@ -396,6 +396,13 @@ int glr_block_params_ok(const glrgtv_shape* s, const glrgtv_block_params* p) {
     return GLRGTV_OK;
 }
 
+// block_stream_fwd.cu
+extern int g_glr_block_path;
+int glr_stream_eligible(const glrgtv_shape* s);
+int glr_launch_gtv_coeffs(const glrgtv_shape& s, const float* w, float* c, void* stream);
+int glr_stream_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, const float* x, float* out,
+                         const glrgtv_block_saved* sv, void* stream);
+
 extern "C" int glrgtv_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, const float* x,
                                 const float* feat0, const float* feat1, float* out, const glrgtv_block_saved* sv,
                                 void* stream) {
@@ -415,6 +422,15 @@ extern "C" int glrgtv_block_fwd(const glrgtv_shape* s, const glrgtv_block_params
     sc.H /= 2; sc.W /= 2;
     if ((rc = launch_weights(*s, feat0, p->gtv0.multiM, p->glr0.multiM, sv->wT0, sv->wL0, stream))) return rc;
     if ((rc = launch_weights(sc, feat1, p->gtv1.multiM, p->glr1.multiM, sv->wT1, sv->wL1, stream))) return rc;
+
+    // register-streaming stage kernels (block_stream_fwd.cu) where the shape allows, else the plane kernels below
+    const bool can_stream = glr_stream_eligible(s) && sv->cT0 && sv->cT1 && glr_aligned16(sv->cT0) && glr_aligned16(sv->cT1);
+    if (g_glr_block_path == 2 && !can_stream) return GLRGTV_ERR_UNSUPPORTED;
+    if (can_stream && g_glr_block_path != 1) {
+        if ((rc = glr_launch_gtv_coeffs(*s, sv->wT0, sv->cT0, stream))) return rc;
+        if ((rc = glr_launch_gtv_coeffs(sc, sv->wT1, sv->cT1, stream))) return rc;
+        return glr_stream_block_fwd(s, p, x, out, sv, stream);
+    }
 
     BlockFwdArgs a;
     a.s = *s; a.p = *p;

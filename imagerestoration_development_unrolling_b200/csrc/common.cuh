@@ -33,7 +33,29 @@ struct emu_dim3 {
 typedef emu_dim3 dim3;
 extern thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 extern thread_local float* emu_smem;  // 256 KB scratch playing the role of dynamic shared memory
-static inline void __syncthreads() {}
+// fiber mode (GLR_LAUNCH_FIBERS): every CUDA thread of a block is a cooperative fiber, so __syncthreads() and the
+// warp shuffles have their real meaning.  Outside fiber mode a block is one thread and the barrier is a no-op.
+extern thread_local bool emu_fiber_mode;
+void emu_barrier();
+float emu_shfl(float v, int src_lane);   // value of `v` held by lane `src_lane` of the caller's warp
+void emu_run_block(unsigned nthreads, void (*fn)(void*), void* arg);
+static inline void __syncthreads() { if (emu_fiber_mode) emu_barrier(); }
+static inline float __shfl_sync(unsigned, float v, int src, int width = 32) {
+    const int lane = (int)(threadIdx.x & 31u);
+    return emu_shfl(v, (lane / width) * width + (src % width));
+}
+static inline float __shfl_up_sync(unsigned, float v, unsigned d, int width = 32) {
+    const int lane = (int)(threadIdx.x & 31u);
+    return emu_shfl(v, (lane % width) >= (int)d ? lane - (int)d : lane);
+}
+static inline float __shfl_down_sync(unsigned, float v, unsigned d, int width = 32) {
+    const int lane = (int)(threadIdx.x & 31u);
+    return emu_shfl(v, (lane % width) + (int)d < width ? lane + (int)d : lane);
+}
+static inline float __shfl_xor_sync(unsigned, float v, int m, int width = 32) {
+    const int lane = (int)(threadIdx.x & 31u);
+    return emu_shfl(v, lane ^ m);
+}
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline float __ldg(const float* p) { return *p; }
 typedef void* cudaStream_t;
@@ -51,6 +73,20 @@ typedef void* cudaStream_t;
                     kernel(__VA_ARGS__);                                               \
                 }                                                                      \
     } while (0)
+// launch with real per-thread semantics: blockDim.x fibers per block (kernels that use shuffles / barriers)
+#define GLR_LAUNCH_FIBERS(kernel, grid, block, smem_bytes, stream, ...)                \
+    do {                                                                               \
+        emu_dim3 g_ = (grid);                                                          \
+        gridDim = g_;                                                                  \
+        blockDim = emu_dim3((block), 1, 1);                                            \
+        auto body_ = [&]() { kernel(__VA_ARGS__); };                                   \
+        for (unsigned bx_ = 0; bx_ < g_.x; ++bx_) {                                    \
+            blockIdx = emu_dim3(bx_, 0, 0);                                            \
+            emu_run_block(blockDim.x, [](void* p_) { (*(decltype(body_)*)p_)(); }, &body_); \
+        }                                                                              \
+        blockDim = emu_dim3(1, 1, 1);                                                  \
+        threadIdx = emu_dim3(0, 0, 0);                                                 \
+    } while (0)
 #define GLR_CHECK_LAUNCH() GLRGTV_OK
 #define GLR_PROF_BEGIN(slot, stream) ((void)0)
 #define GLR_PROF_END(slot, stream) ((void)0)
@@ -62,6 +98,7 @@ static inline int glr_memset_async(void* p, int v, size_t n, cudaStream_t) { mem
 extern unsigned long long g_glr_launches;  // kernels launched by this library (bench.py reports it)
 #define GLR_LAUNCH(kernel, grid, block, smem_bytes, stream, ...) \
     (++g_glr_launches, kernel<<<(grid), (block), (smem_bytes), (cudaStream_t)(stream)>>>(__VA_ARGS__))
+#define GLR_LAUNCH_FIBERS GLR_LAUNCH
 int glr_record_launch_error(void);
 // optional per-kernel timing (glrgtv_profile_*): event pairs recorded on the launching stream
 void glr_prof_mark(int slot, int end, void* stream);

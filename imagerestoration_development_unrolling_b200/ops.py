@@ -395,7 +395,7 @@ gather_neighbors.register_autograd(lambda ctx, g: (gather_neighbors_bwd(g, ctx.e
 # params layout: for each of GTVmodule00, GLRmodule00, GTVmodule01, GLRmodule01: p01, p02a, p02b, p03, multiM (20),
 # then alphaCGD, betaCGD, muys00, ro00, gamma00, muys01, ro01, gamma01 (8), then optionally skip_weight (1).
 _N_BLOCK_PARAMS = 28
-_SAVED = ("wT0", "wL0", "wT1", "wL1", "bA", "x1", "bB", "r1", "x2")
+_SAVED = ("wT0", "wL0", "wT1", "wL1", "bA", "x1", "bB", "r1", "x2", "cT0", "cT1")
 
 
 def _block_structs(params: Sequence[Tensor]):
@@ -418,12 +418,13 @@ def _block_geometry(x: Tensor, n_graphs: int):
 
 
 def _saved_shapes(B, G, F, H, W):
-    return [(B, G, 4, H, W)] * 2 + [(B, G, 4, H // 2, W // 2)] * 2 + [(B, G, F, H, W)] * 5
+    return ([(B, G, 4, H, W)] * 2 + [(B, G, 4, H // 2, W // 2)] * 2 + [(B, G, F, H, W)] * 5 +
+            [(B, G, 2, H, W), (B, G, 2, H // 2, W // 2)])
 
 
 @torch.library.custom_op(f"{_NS}::lowpass_block_fwd", mutates_args=())
 def lowpass_block_fwd(x: Tensor, feat0: Tensor, feat1: Tensor, params: Sequence[Tensor], n_graphs: int) -> List[Tensor]:
-    """-> [out, wT0, wL0, wT1, wL1, bA, x1, bB, r1, x2]   (glrgtv_block_fwd; 6 kernel launches)"""
+    """-> [out, wT0, wL0, wT1, wL1, bA, x1, bB, r1, x2, cT0, cT1]   (glrgtv_block_fwd; 6 kernel launches)"""
     _chk(x, feat0, feat1, *params)
     if len(params) not in (_N_BLOCK_PARAMS, _N_BLOCK_PARAMS + 1):
         raise RuntimeError("lowpass_block: expected 28 (+1 skip) parameter tensors")

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLRGTV_ABI_VERSION 1
+#define GLRGTV_ABI_VERSION 2
 #define GLRGTV_MAX_EDGES 48 /* 7x7 full window */
 
 typedef enum glrgtv_status {
@@ -192,11 +192,19 @@ typedef struct glrgtv_block_grads {
 
 /* activations kept between forward and backward (all written by glrgtv_block_fwd, caller-owned):
  *   w  : 4 weight sets  wT0,wL0 [B,G,4,H,W]  wT1,wL1 [B,G,4,H/2,W/2]
- *   bA, x1, bB, r1, x2 : [B,G,F,H,W] each                                    */
+ *   bA, x1, bB, r1, x2 : [B,G,F,H,W] each                                   
+ *   cT : symmetric GTV coefficients of wT (cR = wR^2 + wL[.,w+1]^2, cD = wD^2 + wU[h+1,.]^2):
+ *        cT0 [B,G,2,H,W], cT1 [B,G,2,H/2,W/2]; read by the register-streaming stage kernels */
 typedef struct glrgtv_block_saved {
     float *wT0, *wL0, *wT1, *wL1;
     float *bA, *x1, *bB, *r1, *x2;
+    float *cT0, *cT1;
 } glrgtv_block_saved;
+
+/* Which kernels the fused block entry points use: 0 = automatic (register-streaming kernels when W % 8 == 0 and
+ * W <= 256, shared-memory plane kernels otherwise), 1 = plane kernels only, 2 = streaming kernels only
+ * (GLRGTV_ERR_UNSUPPORTED for other shapes).  A debugging / test switch; both paths compute the same function. */
+int glrgtv_set_block_path(int mode);
 
 /* x [B,C,H,W]; feat0 = patchs_features_extraction00(x) [B,2C,H,W]; feat1 = ..01(x) [B,2C,H/2,W/2]
  * (first C channels feed GTV, last C feed GLR, V1X0:714, 726);  out [B,C,H,W]. */

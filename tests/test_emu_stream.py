@@ -1,0 +1,43 @@
+"""Register-streaming block kernels (csrc/block_stream_*.cu) in the g++ emulation build (fibers give the warp
+shuffles and barriers their real meaning) against the oracle.  The path is forced with glrgtv_set_block_path(2)."""
+import pytest
+import torch
+
+from oracle import glr_gtv_oracle as O
+from imagerestoration_development_unrolling_b200 import _lib as L
+from tests import emu_harness as E
+from tests.util import (rel, random_block_state, block_structs, alloc_saved, oracle_features, alloc_grads,
+                        grads_to_state_names)
+
+# (dim, ngraphs, B, H, W): every walker width (8/16/32/64 lanes), partial walkers (W=24, 48, 136), bands, tiny planes
+CASES = [(12, 2, 2, 12, 16), (6, 1, 1, 10, 8), (12, 2, 1, 20, 24), (12, 4, 1, 14, 40), (6, 2, 1, 8, 64),
+         (6, 1, 1, 12, 72), (6, 2, 1, 6, 128), (3, 1, 1, 8, 136), (2, 1, 1, 6, 256), (24, 2, 1, 2, 8)]
+
+
+@pytest.fixture(autouse=True)
+def stream_path():
+    E.emu_lib().glrgtv_set_block_path(2)
+    yield
+    E.emu_lib().glrgtv_set_block_path(0)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_stream_block_forward(case):
+    dim, G, B, H, W = case
+    F = dim // G
+    sd = random_block_state(dim, G, seed=300 + H)
+    x = torch.randn(B, dim, H, W, generator=torch.Generator().manual_seed(H * W))
+    ref_out, inter = O.mixture_gtvglr_forward({k: v.double() for k, v in sd.items()}, x.double(), "local_filter.",
+                                              return_intermediates=True)
+    s = sd["skip_weight"].double()
+    ref_out = s[0] * x.double() + s[1] * ref_out
+    f0, f1 = oracle_features(sd, x)
+    p, keep = block_structs(sd)
+    sv, saved = alloc_saved(B, G, F, H, W)
+    out = torch.empty_like(x)
+    E.call("glrgtv_block_fwd", L.make_shape(B, G, F, H, W), p, x, f0, f1, out, sv, None)
+    for n in ("wT0", "wL0", "wT1", "wL1"):
+        assert rel(saved[n], inter[n]) < 5e-6, n
+    for n in ("bA", "x1", "bB", "r1", "x2"):
+        assert rel(saved[n], inter[n]) < 2e-5, (n, rel(saved[n], inter[n]))
+    assert rel(out, ref_out) < 1e-5
