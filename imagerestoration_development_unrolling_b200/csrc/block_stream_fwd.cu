@@ -36,81 +36,222 @@ struct StreamFwdArgs {
 // one resolution of one walker
 struct Lvl {
     int H, W;
-    const float* z;      // channel plane of the stage input AT THE FINE resolution (the coarse walker pools it)
-    const float* wL;     // [4][H][W] of this (b, g)
-    const float* wT;     // [4][H][W]
-    const float* cT;     // [2][H][W]
     StatsTaps kL, kT;
     float aL, aT, Gam;
 };
 
+// Shared-memory staging.  Every global operand reaches the walkers through rings that ONE elected thread fills with
+// TMA bulk copies (cp.async.bulk, whole image rows, completion counted on an mbarrier) two to three block steps ahead of
+// their use, so no walker ever issues or waits on a global load of its own:
+//   zring  [nch][ZR][Wp]          stage-input rows; the coarse walker meets them first (pooling two per coarse row), the
+//                                 fine walker reads them again DF steps later: z is loaded once
+//   opring [nch][NOP][OPR][Wp]    epilogue operands (X2: y | X3: x, bB, r1)
+//   w0ring [NPL][WR][Wp], w1ring [NPL][WR][Wp/2]   weight / coefficient rows of this (batch, graph), ONE copy per CTA
+//                                 shared by its channel walkers; plane order: cT(2), wL(4) if GLR, wT(4) if THR.
+//                                 The wT plane U is staged one row ahead (its row r+1 feeds the thresholded core).
+//   cring  [nch][2][NRING][Wp/2]  coarse result -> fine epilogue hand-over
+// Copies are issued in BATCHES: batch j = everything block steps 2j-1 and 2j read, issued at the odd step 2j-3 by lane 0
+// of the first coarse warp (coarse walkers rest on odd steps), tracked by mbarrier j % 4.
+#ifndef STREAM_MAXT
+#define STREAM_MAXT 192   // threads per CTA (fine + coarse walkers)
+#endif
+#ifndef STREAM_MINB
+#define STREAM_MINB 2     // resident CTAs per SM the register budget is sized for
+#endif
+#define STREAM_ZR 14
+#define STREAM_OPR 4
+#define STREAM_WR 4
+#define STREAM_NBAR 4
+#define STREAM_PD 2      // cp.async loader: block steps between issuing a copy and reading it
+#define STREAM_MAXJ 5    // cp.async loader: weight-plane copies per thread and step held as precomputed descriptors
 template <int MODE>
-struct WState {
-    Row z1, z2, z3;          // input rows t-1, t-2, t-3
-    Row sA1, sA2, sB1, sB2;  // S rows t-2, t-3
-    Row lA1, lA2, oB1, oB2;  // core rows t-3, t-4
-    Row oT1, oT2;            // thresholded core (X2)
-    Row cDp;                 // cD coefficients of core row t-3
+struct StreamSmem {
+    static constexpr bool GLR = MODE != MODE_BA, THR = MODE == MODE_X2;
+    static constexpr int NOP = MODE == MODE_X2 ? 1 : MODE == MODE_X3 ? 3 : 0;
+    static constexpr int NPL = 2 + (GLR ? 4 : 0) + (THR ? 4 : 0);
+    static constexpr int NRING = THR ? 2 : 1;
+    static constexpr int PL_C = 0, PL_WL = 2, PL_WT = 2 + (GLR ? 4 : 0);
+    int Wp, nch;
+    __host__ __device__ size_t bars() const { return 0; }                       // STREAM_NBAR x 8 bytes
+    __host__ __device__ size_t zring() const { return 2 * STREAM_NBAR; }
+    __host__ __device__ size_t opring() const { return zring() + (size_t)nch * STREAM_ZR * Wp; }
+    __host__ __device__ size_t w0ring() const { return opring() + (size_t)nch * NOP * STREAM_OPR * Wp; }
+    __host__ __device__ size_t w1ring() const { return w0ring() + (size_t)NPL * STREAM_WR * Wp; }
+    __host__ __device__ size_t cring() const { return w1ring() + (size_t)NPL * STREAM_WR * (Wp / 2); }
+    __host__ __device__ size_t mbox() const { return cring() + (size_t)nch * 2 * NRING * (Wp / 2); }
+    __host__ __device__ size_t total() const { return mbox() + (size_t)2 * nch * PL_COUNT * 2 + 8; }
 };
 
-template <int MODE, bool XW>
-__global__ void __launch_bounds__(384) k_stream_fwd(StreamFwdArgs a) {
-    GLR_SMEM_DECL(smem);
-    constexpr bool GLR = MODE != MODE_BA, THR = MODE == MODE_X2;
-    constexpr int NRING = THR ? 2 : 1;
-    const int H = a.s.H, W = a.s.W, F = a.s.F, G = a.s.G;
-    const int GL = XW ? 64 : (W <= 32 ? 8 : W <= 64 ? 16 : 32), GLc = GL / 2;
-    const int nch = a.nch;
-    const int NTF = (nch * GL + 31) & ~31;      // fine threads first, then coarse threads (roles never share a warp)
-    const int tid = (int)threadIdx.x;
-    const bool fine = tid < NTF;
-    const int gl = fine ? GL : GLc;
-    const int wk = fine ? tid / GL : (tid - NTF) / GLc;          // walker == channel slot
-    const int lane = fine ? tid % GL : (tid - NTF) % GLc;
-    const bool live = wk < nch;
-
-    // block -> (band, channel chunk, graph, batch)
+// geometry of one CTA, shared by the walkers and the producer
+struct StreamCta {
+    int H, W, F, G, nch, b, g, f0, R0, R1, K0, M, Wp;
+    size_t HW;
+};
+__device__ __forceinline__ StreamCta stream_cta(const StreamFwdArgs& a, int GL) {
+    StreamCta c;
+    c.H = a.s.H; c.W = a.s.W; c.F = a.s.F; c.G = a.s.G; c.nch = a.nch;
     int bid = (int)blockIdx.x;
     const int band = bid % a.n_bands; bid /= a.n_bands;
-    const int chunks = F / nch;
+    const int chunks = c.F / c.nch;
     const int chunk = bid % chunks; bid /= chunks;
-    const int g = bid % G, b = bid / G;
-    const int f = chunk * nch + (live ? wk : 0), c = g * F + f;
-    const int R0 = band * a.band_rows, R1 = R0 + a.band_rows < H ? R0 + a.band_rows : H;
-    const size_t HW = (size_t)H * W, HWc = HW / 4;
-    const size_t plane = (size_t)b * G + g;
-    const size_t off = ((size_t)b * G * F + c) * HW;
+    c.g = bid % c.G; c.b = bid / c.G;
+    c.f0 = chunk * c.nch;
+    c.R0 = band * a.band_rows;
+    c.R1 = c.R0 + a.band_rows < c.H ? c.R0 + a.band_rows : c.H;
+    c.K0 = c.R0 / 2;
+    c.M = (c.R1 - c.R0) + 6 + STREAM_DF;
+    c.Wp = 4 * GL;
+    c.HW = (size_t)c.H * c.W;
+    return c;
+}
 
-    // shared memory: ring [nch][2 slots][NRING][2*GL]  |  mailboxes [2][nch][PL_COUNT][2]
-    const int ringW = 2 * GL;
-    float* ring = smem + (size_t)wk * 2 * NRING * ringW;
-    float* mbox = smem + (size_t)nch * 2 * NRING * ringW;
+// ---- the producer: all global -> shared traffic of batch j (block steps 2j-1 and 2j), as TMA bulk row copies.
+// The 32 lanes of the first coarse warp share the batch's item list
+//     [fine items of step 2j-1 | fine items of step 2j | coarse items of step 2j],
+//     fine items = NPL weight rows + nch*NOP operand rows, coarse items = NPL weight rows + 2*nch input rows;
+// lane l owns items l, l+32, ...  An item's row is an affine function of j, so each lane decodes its items ONCE into
+// descriptors and a batch costs it a handful of instructions per copy.
+#define STREAM_MAXI 4
+struct ProdItem {
+    const float* src0;   // row 0 of the source plane (nullptr: no item)
+    int dst0;            // ring base, floats from the start of shared memory
+    int r_off, rstep;    // row = r_off + rstep * j
+    int lo, hi;          // copy iff lo <= row < hi
+    int pitch;           // floats per source row (= bytes / 4 of one copy)
+    int rpitch;          // ring row pitch in floats; < 0: the z ring (slot = (2j mod ZR) + k, pitch -rpitch)
+};
+template <int MODE>
+__device__ __forceinline__ ProdItem stream_item(const StreamFwdArgs& a, const StreamCta& c, int it) {
+    using SM = StreamSmem<MODE>;
+    constexpr int NOP = SM::NOP, NPL = SM::NPL, ZR = STREAM_ZR;
+    SM lay; lay.Wp = c.Wp; lay.nch = c.nch;
+    const int Wp = c.Wp, Wpc = Wp / 2, H = c.H, W = c.W, Hc = H / 2, Wc = W / 2;
+    const size_t HW = c.HW, HWc = HW / 4, plane = (size_t)c.b * c.G + c.g;
+    const size_t off0 = ((size_t)c.b * c.G * c.F + (size_t)c.g * c.F + c.f0) * HW;     // first channel of this CTA
+    const bool has_skip = MODE == MODE_X3 && a.p.skip != nullptr;
+    const int NF = NPL + c.nch * NOP, NC = NPL + 2 * c.nch, NI = 2 * NF + NC;
+    ProdItem p;
+    p.src0 = nullptr; p.dst0 = 0; p.r_off = 0; p.rstep = 0; p.lo = 0; p.hi = 0; p.pitch = 0; p.rpitch = 0;
+    if (it >= NI) return p;
+    const bool coarse = it >= 2 * NF;
+    const int s = coarse ? 1 : (it >= NF ? 1 : 0);                  // block step mt = 2j - 1 + s
+    int idx = coarse ? it - 2 * NF : (it >= NF ? it - NF : it);
+    // newest row of the consuming walker at step mt: fine t = R0-3 + mt-DF, coarse t = K0-3 + mt/2; mt in [DF or 0, M)
+    const int t_off = coarse ? c.K0 - 3 : c.R0 - 4 - STREAM_DF + s;    // t = t_off + (coarse ? j : 2j)
+    const int t_lo = coarse ? c.K0 - 3 : c.R0 - 3;                     // t at the first step that consumes
+    const int t_hi = coarse ? c.K0 - 3 + ((c.M + 1) >> 1) : c.R0 - 3 + c.M - STREAM_DF;   // one past the last
+    p.rstep = coarse ? 1 : 2;
+    if (idx < NPL) {                                     // weight / coefficient row of the core row t-2
+        const int set = idx < 2 ? 0 : (SM::GLR && idx < 6) ? 1 : 2;
+        const int e = idx - (set == 0 ? 0 : set == 1 ? SM::PL_WL : SM::PL_WT);
+        const int d = -2 + ((set == 2 && e == 0) ? 1 : 0);
+        p.r_off = t_off + d;
+        p.lo = glr_maxi(0, t_lo + d); p.hi = glr_mini(coarse ? Hc : H, t_hi + d);
+        if (coarse) {
+            p.src0 = (set == 0 ? a.cT1 + plane * 2 * HWc : (set == 1 ? a.wL1 : a.wT1) + plane * 4 * HWc) + (size_t)e * HWc;
+            p.dst0 = (int)lay.w1ring() + idx * STREAM_WR * Wpc; p.pitch = Wc; p.rpitch = Wpc;
+        } else {
+            p.src0 = (set == 0 ? a.cT0 + plane * 2 * HW : (set == 1 ? a.wL0 : a.wT0) + plane * 4 * HW) + (size_t)e * HW;
+            p.dst0 = (int)lay.w0ring() + idx * STREAM_WR * Wp; p.pitch = W; p.rpitch = Wp;
+        }
+        return p;
+    }
+    idx -= NPL;
+    if (coarse) {                                        // the two fine rows coarse row t pools, per channel: rho = 2t + k
+        const int ch = idx >> 1, k = idx & 1;
+        p.src0 = a.z + off0 + (size_t)ch * HW;
+        p.r_off = 2 * t_off + k; p.rstep = 2;
+        p.lo = glr_maxi(0, 2 * t_lo + k); p.hi = glr_mini(H, 2 * (t_hi - 1) + k + 1);
+        p.dst0 = (int)lay.zring() + (ch * ZR + k) * Wp; p.pitch = W; p.rpitch = -Wp;
+        return p;
+    }
+    if (NOP > 0) {                                       // epilogue operands of row t-3, per channel
+        const int ch = idx / NOP, k = idx - ch * NOP;
+        if (MODE == MODE_X3 && k == 0 && !has_skip) return p;
+        p.src0 = (k == 0 ? a.y : k == 1 ? a.bB_in : a.r1_in) + off0 + (size_t)ch * HW;
+        p.r_off = t_off - 3;
+        p.lo = glr_maxi(c.R0, t_lo - 3); p.hi = glr_mini(c.R1, t_hi - 3);
+        p.dst0 = (int)lay.opring() + (ch * NOP + k) * STREAM_OPR * Wp; p.pitch = W; p.rpitch = Wp;
+    }
+    return p;
+}
+// issue batch j: called by all 32 producer lanes
+__device__ __forceinline__ void stream_produce(const ProdItem (&items)[STREAM_MAXI], float* smem, int bars_off, int j, int pl_lane) {
+    const smem_addr_t sbase = smem_addr(smem);
+    const smem_addr_t bar = smem_advance(sbase, bars_off + 2 * (j & (STREAM_NBAR - 1)));
+    int row[STREAM_MAXI];
+    unsigned bytes = 0;
+#pragma unroll
+    for (int i = 0; i < STREAM_MAXI; ++i) {
+        row[i] = items[i].r_off + items[i].rstep * j;
+        if (items[i].src0 != nullptr && row[i] >= items[i].lo && row[i] < items[i].hi) bytes += 4u * (unsigned)items[i].pitch;
+        else row[i] = -1;
+    }
+    // total over the warp (exact in fp32 far beyond any batch size), then arm the barrier before the copies fly
+    float fb = (float)bytes;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fb += __shfl_xor_sync(0xffffffffu, fb, o);
+    if (pl_lane == 0) mbar_expect_tx(bar, (unsigned)fb);
+    __syncwarp();
+    const int zslot = (2 * j) % STREAM_ZR;
+#pragma unroll
+    for (int i = 0; i < STREAM_MAXI; ++i) {
+        if (row[i] < 0) continue;
+        const int slot_off = items[i].rpitch < 0 ? zslot * (-items[i].rpitch) : (row[i] & (STREAM_WR - 1)) * items[i].rpitch;
+        bulk_g2s(smem_advance(sbase, items[i].dst0 + slot_off), items[i].src0 + (size_t)row[i] * items[i].pitch,
+                 4u * (unsigned)items[i].pitch, bar);
+    }
+}
+
+// The walk of one role.  FINE / COARSE are separate instantiations (their warps never mix), so each loop is
+// specialised; both execute exactly M block barriers.  The row windows are 3-cycles indexed by the compile-time phase
+// of the unrolled step, so no register is ever moved to "rotate" a window.
+template <int MODE, bool XW, bool FINE, bool TMA>
+__device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem, const int wk, const int nwk, const int lane,
+                                            const int GL) {
+    using SM = StreamSmem<MODE>;
+    constexpr bool GLR = SM::GLR, THR = SM::THR;
+    constexpr int NRING = SM::NRING, NOP = SM::NOP, NPL = SM::NPL, ZR = STREAM_ZR, PD = STREAM_PD;
+    const StreamCta ct = stream_cta(a, GL);
+    const int H = ct.H, W = ct.W, G = ct.G, nch = ct.nch, g = ct.g, R0 = ct.R0, R1 = ct.R1, M = ct.M;
+    const bool live = wk < nch;
+    const int c = g * ct.F + ct.f0 + (live ? wk : 0);
+    const size_t off = ((size_t)ct.b * G * ct.F + c) * ct.HW;
+
+    SM lay; lay.Wp = ct.Wp; lay.nch = nch;
+    const int Wp = ct.Wp, Wpc = Wp / 2;
+    const float* zring = smem + lay.zring() + (size_t)(live ? wk : 0) * ZR * Wp;              // this walker's channel
+    const float* opring = smem + lay.opring() + (size_t)(live ? wk : 0) * NOP * STREAM_OPR * Wp;
+    const float* wring = smem + (FINE ? lay.w0ring() : lay.w1ring());                          // this role's level
+    float* cring = smem + lay.cring() + (size_t)(live ? wk : 0) * 2 * NRING * Wpc;
+    float* mbox = smem + lay.mbox();
+    const smem_addr_t bars = smem_advance(smem_addr(smem), (int)lay.bars());
+    const int wpitch = FINE ? Wp : Wpc;                                                  // row pitch of this level's weight ring
+    const int GLc_ = GL / 2;
+    const int pw_lane = wk * GLc_ + lane;                  // lane within the first coarse warp (valid when < 32)
+    const bool producer = TMA && !FINE && pw_lane < 32;
 
     Lvl L;
-    if (fine) {
+    if (FINE) {
         L.H = H; L.W = W;
-        L.wL = a.wL0 + plane * 4 * HW; L.wT = a.wT0 + plane * 4 * HW; L.cT = a.cT0 + plane * 2 * HW;
         L.kT = glr_load_taps(a.p.gtv0.stats, c);
         L.kL = GLR ? glr_load_taps(a.p.glr0.stats, c) : L.kT;
         L.aT = expf(a.p.ro0[g]); L.aL = GLR ? expf(a.p.mu0[g]) : 0.f; L.Gam = THR ? expf(a.p.gamma0[g]) : 0.f;
     } else {
         L.H = H / 2; L.W = W / 2;
-        L.wL = a.wL1 + plane * 4 * HWc; L.wT = a.wT1 + plane * 4 * HWc; L.cT = a.cT1 + plane * 2 * HWc;
         L.kT = glr_load_taps(a.p.gtv1.stats, c);
         L.kL = GLR ? glr_load_taps(a.p.glr1.stats, c) : L.kT;
         L.aT = expf(a.p.ro1[g]); L.aL = GLR ? expf(a.p.mu1[g]) : 0.f; L.Gam = THR ? expf(a.p.gamma1[g]) : 0.f;
     }
-    L.z = a.z + off;
-    const size_t LHW = (size_t)L.H * L.W;
 
     LaneCtx lc;
     lc.col0 = 4 * lane;
-    lc.width = gl < 32 ? gl : 32;
+    lc.width = FINE ? (GL < 32 ? GL : 32) : (GL / 2 < 32 ? GL / 2 : 32);
     lc.active = live && lc.col0 < L.W;
     lc.first = lc.col0 == 0;
     lc.last = lc.col0 + 4 >= L.W;
-    lc.seam_l = XW && live && fine && lane == 32 && lc.col0 < L.W;
-    lc.seam_r = XW && live && fine && lane == 31 && lc.col0 + 4 < L.W;
+    lc.seam_l = XW && FINE && live && lane == 32 && lc.col0 < L.W;
+    lc.seam_r = XW && FINE && live && lane == 31 && lc.col0 + 4 < L.W;
     lc.mb_rd = lc.mb_wr = mbox;
 
     float alpha = 0.f, beta2 = 0.f, s0 = 0.f, s1 = 1.f;
@@ -123,170 +264,338 @@ __global__ void __launch_bounds__(384) k_stream_fwd(StreamFwdArgs a) {
     }
     const bool has_skip = MODE == MODE_X3 && a.p.skip != nullptr;
 
-    WState<MODE> st;
-    st.z1 = st.z2 = st.z3 = st.sA1 = st.sA2 = st.sB1 = st.sB2 = st.lA1 = st.lA2 = st.oB1 = st.oB2 = st.oT1 = st.oT2 = st.cDp = row_zero();
+    const int r0 = FINE ? R0 : ct.K0;
+    auto wrow = [&](int pl, int row) { return wring + (pl * STREAM_WR + (row & (STREAM_WR - 1))) * wpitch + lc.col0; };
 
-    // the walker's row range at its own resolution and the first row it loads
-    const int r0 = fine ? R0 : R0 / 2, r1 = fine ? R1 : R1 / 2;
-    const int M = (R1 - R0) + 6 + STREAM_DF;
-
-    for (int m = 0; m < M; ++m) {
-        const bool stepping = fine ? (m >= STREAM_DF) : ((m & 1) == 0);
-        if (stepping) {
-            const int t = r0 - 3 + (fine ? m - STREAM_DF : (m >> 1));     // newest row of this step
-            if (XW) {
-                lc.mb_rd = mbox + (size_t)((m + 1) & 1) * nch * PL_COUNT * 2 + (size_t)wk * PL_COUNT * 2;
-                lc.mb_wr = mbox + (size_t)(m & 1) * nch * PL_COUNT * 2 + (size_t)wk * PL_COUNT * 2;
+    // ---- cp.async loader (TMA == false): every thread stages its own share STREAM_PD block steps ahead.
+    //      weight planes wk, wk+nwk, ... of this role's level (src at row 0, ring address, row lead), this lane's quad
+    const smem_addr_t sbase = smem_addr(smem);
+    const float* wsrc[STREAM_MAXJ];
+    smem_addr_t wdst[STREAM_MAXJ];
+    bool wlead[STREAM_MAXJ];
+    const float* opp[3] = {nullptr, nullptr, nullptr};
+    const float* zpp = a.z + off + 2 * lc.col0;
+    int zis = 0;                                           // ring slot of the next pooled row pair to stage
+    if (!TMA) {
+        const size_t plane = (size_t)ct.b * G + g;
+        const int LHW = L.H * L.W;
+        const bool copier = lc.col0 < L.W;                 // dead walkers help with the shared weight copies
+#pragma unroll
+        for (int j = 0; j < STREAM_MAXJ; ++j) {
+            const int pl = wk + j * nwk;
+            wsrc[j] = nullptr; wdst[j] = sbase; wlead[j] = false;
+            if (copier && pl < NPL) {
+                const int set = pl < 2 ? 0 : (GLR && pl < 6) ? 1 : 2;
+                const int e = pl - (set == 0 ? 0 : set == 1 ? SM::PL_WL : SM::PL_WT);
+                const float* base = FINE ? (set == 0 ? a.cT0 + plane * 2 * LHW : (set == 1 ? a.wL0 : a.wT0) + plane * 4 * LHW)
+                                         : (set == 0 ? a.cT1 + plane * 2 * LHW : (set == 1 ? a.wL1 : a.wT1) + plane * 4 * LHW);
+                wsrc[j] = base + (size_t)e * LHW + lc.col0;
+                wdst[j] = smem_advance(sbase, (int)(FINE ? lay.w0ring() : lay.w1ring()) + pl * STREAM_WR * wpitch + lc.col0);
+                wlead[j] = set == 2 && e == 0;             // wT plane U runs one row ahead
             }
-            // ---- load row t (fine: the row itself; coarse: the 2x2 mean of fine rows 2t, 2t+1)
-            Row zn = row_zero();
-            if (lc.active && t >= 0 && t < L.H) {
-                if (fine) {
-                    zn = row_ld(L.z + (size_t)t * W + lc.col0);
+        }
+        if (FINE && lc.active) {
+            if (MODE == MODE_X2 || has_skip) opp[0] = a.y + off + lc.col0;
+            if (MODE == MODE_X3) { opp[1] = a.bB_in + off + lc.col0; opp[2] = a.r1_in + off + lc.col0; }
+        }
+    }
+    const smem_addr_t opdst = smem_advance(sbase, (int)lay.opring() + (live ? wk : 0) * NOP * STREAM_OPR * Wp + lc.col0);
+    const smem_addr_t zdst = smem_advance(sbase, (int)lay.zring() + (live ? wk : 0) * ZR * Wp + 2 * lc.col0);
+    auto issue = [&](int mt) {
+        if (mt >= M) return;
+        if (FINE ? (mt < STREAM_DF) : (mt & 1)) return;
+        const int t = r0 - 3 + (FINE ? mt - STREAM_DF : (mt >> 1));
+        if (!FINE) {
+            // the two fine rows the coarse row t pools (this lane's 8 columns)
+            if (lc.active) {
+                const int rho = 2 * t;
+                const smem_addr_t d = smem_advance(zdst, zis * Wp);
+                const float* src = zpp + (size_t)rho * W;
+                if (rho >= 0 && rho < H) { cp_async16_s(d, src); cp_async16_s(smem_advance(d, 4), src + 4); }
+                if (rho + 1 >= 0 && rho + 1 < H) { cp_async16_s(smem_advance(d, Wp), src + W); cp_async16_s(smem_advance(d, Wp + 4), src + W + 4); }
+            }
+            zis = zis + 2 == ZR ? 0 : zis + 2;
+        } else if (NOP > 0) {
+            const int re = t - 3;                          // epilogue operands of row t-3
+            if (re >= R0 && re < R1) {
+                const int so = (re & (STREAM_OPR - 1)) * Wp, go = re * W;
+#pragma unroll
+                for (int k = 0; k < NOP; ++k)
+                    if (opp[k] != nullptr) cp_async16_s(smem_advance(opdst, k * STREAM_OPR * Wp + so), opp[k] + go);
+            }
+        }
+        // weight / coefficient rows of the core row t-2 of this level, shared by the CTA's channel walkers
+        const int rw = t - 2;
+        const bool ok0 = rw >= 0 && rw < L.H, ok1 = rw + 1 >= 0 && rw + 1 < L.H;
+        const int so0 = (rw & (STREAM_WR - 1)) * wpitch, so1 = ((rw + 1) & (STREAM_WR - 1)) * wpitch;
+        const int go0 = rw * L.W, go1 = go0 + L.W;
+#pragma unroll
+        for (int j = 0; j < STREAM_MAXJ; ++j) {
+            if (wsrc[j] == nullptr) continue;
+            if (wlead[j]) { if (ok1) cp_async16_s(smem_advance(wdst[j], so1), wsrc[j] + go1); }
+            else if (ok0) cp_async16_s(smem_advance(wdst[j], so0), wsrc[j] + go0);
+        }
+        if (wk + STREAM_MAXJ * nwk < NPL && lc.col0 < L.W) {      // (a CTA with very few walkers: remaining planes, generic path)
+            const size_t plane = (size_t)ct.b * G + g;
+            const int LHW = L.H * L.W;
+            for (int pl = wk + STREAM_MAXJ * nwk; pl < NPL; pl += nwk) {
+                const int set = pl < 2 ? 0 : (GLR && pl < 6) ? 1 : 2;
+                const int e = pl - (set == 0 ? 0 : set == 1 ? SM::PL_WL : SM::PL_WT);
+                const bool lead = set == 2 && e == 0;
+                if (lead ? !ok1 : !ok0) continue;
+                const float* base = FINE ? (set == 0 ? a.cT0 + plane * 2 * LHW : (set == 1 ? a.wL0 : a.wT0) + plane * 4 * LHW)
+                                         : (set == 0 ? a.cT1 + plane * 2 * LHW : (set == 1 ? a.wL1 : a.wT1) + plane * 4 * LHW);
+                cp_async16_s(smem_advance(sbase, (int)(FINE ? lay.w0ring() : lay.w1ring()) + pl * STREAM_WR * wpitch + lc.col0 + (lead ? so1 : so0)),
+                             base + (size_t)e * LHW + lc.col0 + (lead ? go1 : go0));
+            }
+        }
+    };
+
+    Row z[3], sA[3], sB[3], lA[3], oB[3], oT[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) z[k] = sA[k] = sB[k] = lA[k] = oB[k] = oT[k] = row_zero();
+    Row cDp = row_zero(), wU_next = row_zero(), wD_prev = row_zero();
+    // ring slots of the rows this walker reads next: fine row t / fine row t-3 / first pooled row (row - (R0-6) mod ZR)
+    int zs = FINE ? STREAM_DF - 5 : 0, zqs = 0;
+
+    if (!TMA) {
+#pragma unroll
+        for (int k = 0; k < PD; ++k) { issue(k); cp_async_commit(); }
+    }
+    ProdItem items[STREAM_MAXI];
+    if (TMA && !FINE) {
+#pragma unroll
+        for (int i = 0; i < STREAM_MAXI; ++i) items[i] = stream_item<MODE>(a, ct, producer ? pw_lane + 32 * i : 1 << 20);
+        if (producer) { stream_produce(items, smem, (int)lay.bars(), 0, pw_lane); stream_produce(items, smem, (int)lay.bars(), 1, pw_lane); }
+    }
+
+    for (int m0 = 0; m0 < M; m0 += 6) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int m = m0 + k;
+            if (m >= M) break;
+            if (TMA) {
+                const int j = (m + 1) >> 1;
+                mbar_wait(smem_advance(bars, 2 * (j & (STREAM_NBAR - 1))), (unsigned)(j >> 2) & 1u);
+            } else {
+                cp_async_wait_pending<PD - 1>();
+            }
+            __syncthreads();
+            if (!TMA) { issue(m + PD); cp_async_commit(); }
+            if (!FINE && (k & 1)) {
+                if (producer) stream_produce(items, smem, (int)lay.bars(), (m + 3) >> 1, pw_lane);
+                continue;
+            }
+            if (FINE && m < STREAM_DF) continue;
+            // window phase: the new row goes to slot N, the centre row (new one step ago) is C, the upper row is U
+            const int N = FINE ? k % 3 : k / 2, C = (N + 2) % 3, U = (N + 1) % 3;
+            const int t = r0 - 3 + (FINE ? m - STREAM_DF : (m >> 1));     // newest row of this step
+            if (XW && FINE) {
+                lc.mb_rd = mbox + ((m + 1) & 1) * nch * PL_COUNT * 2 + wk * PL_COUNT * 2;
+                lc.mb_wr = mbox + (m & 1) * nch * PL_COUNT * 2 + wk * PL_COUNT * 2;
+            }
+            // ---- row t from the staged ring (fine: the row itself; coarse: the 2x2 mean of fine rows 2t, 2t+1).
+            //      clamp extension is applied HERE, when a row is produced: the row above row 0 becomes a copy of row 0
+            //      (written into the centre slot the moment row 0 arrives), rows below the image repeat row H-1.
+            if (t >= 0 && t < L.H) {
+                if (FINE) {
+                    z[N] = row_ld(zring + zs * Wp + lc.col0);
                 } else {
-                    const float* p = L.z + (size_t)(2 * t) * W + 2 * lc.col0;
-                    const Row a0 = row_ld(p), a1 = row_ld(p + 4), b0 = row_ld(p + W), b1 = row_ld(p + W + 4);
-                    zn.v[0] = 0.25f * (a0.v[0] + a0.v[1] + b0.v[0] + b0.v[1]);
-                    zn.v[1] = 0.25f * (a0.v[2] + a0.v[3] + b0.v[2] + b0.v[3]);
-                    zn.v[2] = 0.25f * (a1.v[0] + a1.v[1] + b1.v[0] + b1.v[1]);
-                    zn.v[3] = 0.25f * (a1.v[2] + a1.v[3] + b1.v[2] + b1.v[3]);
+                    const float* p0 = zring + zs * Wp + 2 * lc.col0;
+                    const Row a0 = row_ld(p0), a1 = row_ld(p0 + 4), b0 = row_ld(p0 + Wp), b1 = row_ld(p0 + Wp + 4);
+                    z[N].v[0] = 0.25f * (a0.v[0] + a0.v[1] + b0.v[0] + b0.v[1]);
+                    z[N].v[1] = 0.25f * (a0.v[2] + a0.v[3] + b0.v[2] + b0.v[3]);
+                    z[N].v[2] = 0.25f * (a1.v[0] + a1.v[1] + b1.v[0] + b1.v[1]);
+                    z[N].v[3] = 0.25f * (a1.v[2] + a1.v[3] + b1.v[2] + b1.v[3]);
                 }
+                if (t == 0) z[C] = z[N];
+            } else {
+                z[N] = t < 0 ? row_zero() : z[C];
             }
-            mb_post<XW>(zn, lc, PL_Z);
-            // ---- S at row t-1
-            Row sAn, sBn;
+            mb_post<XW && FINE>(z[N], lc, PL_Z);
+            // ---- S at row t-1 (clamp-extended like z)
             {
                 const int r = t - 1;
-                const Row u = row_sel(r == 0, st.z1, st.z2), d = row_sel(r == L.H - 1, st.z1, zn);
-                float l, rr;
-                nb_lr<false, XW>(st.z1, l, rr, lc, PL_Z);
-                sBn = w_S(L.kT, st.z1, u, d, l, rr);
-                sAn = GLR ? w_S(L.kL, st.z1, u, d, l, rr) : sBn;
-                if (GLR) mb_post<XW>(sAn, lc, PL_SA);
-                mb_post<XW>(sBn, lc, PL_SB);
+                if (r >= 0 && r < L.H) {
+                    float l, rr;
+                    nb_lr<false, XW && FINE>(z[C], l, rr, lc, PL_Z);
+                    sB[N] = w_S(L.kT, z[C], z[U], z[N], l, rr);
+                    if (GLR) sA[N] = w_S(L.kL, z[C], z[U], z[N], l, rr);
+                    if (r == 0) { sB[C] = sB[N]; if (GLR) sA[C] = sA[N]; }
+                } else if (r >= L.H) {
+                    sB[N] = sB[C];
+                    if (GLR) sA[N] = sA[C];
+                }
+                if (GLR) mb_post<XW && FINE>(sA[N], lc, PL_SA);
+                mb_post<XW && FINE>(sB[N], lc, PL_SB);
             }
             // ---- L and the GTV cores at row t-2 (zero rows outside the image)
-            Row lAn = row_zero(), oBn = row_zero(), oTn = row_zero();
             {
                 const int r = t - 2;
-                const bool in = r >= 0 && r < L.H;
-                const bool ld = in && lc.active;
-                const bool top = r == 0, bot = r == L.H - 1;
-                const float* wrow = (const float*)nullptr;
-                if (GLR) {
-                    const Row u = row_sel(top, st.sA1, st.sA2), d = row_sel(bot, st.sA1, sAn);
+                if (r >= 0 && r < L.H) {
                     float l, rr;
-                    nb_lr<false, XW>(st.sA1, l, rr, lc, PL_SA);
-                    Row w[4];
-                    wrow = L.wL + (size_t)(ld ? r : 0) * L.W + (lc.active ? lc.col0 : 0);
+                    if (GLR) {
+                        nb_lr<false, XW && FINE>(sA[C], l, rr, lc, PL_SA);
+                        Row w[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) w[e] = row_ld_if(ld, wrow + e * LHW);
-                    lAn = row_sel(in, w_L(st.sA1, u, d, l, rr, w), lAn);
-                }
-                {
-                    const Row u = row_sel(top, st.sB1, st.sB2), d = row_sel(bot, st.sB1, sBn);
-                    float l, rr;
-                    nb_lr<false, XW>(st.sB1, l, rr, lc, PL_SB);
-                    const float* crow = L.cT + (size_t)(ld ? r : 0) * L.W + (lc.active ? lc.col0 : 0);
-                    const Row cr = row_ld_if(ld, crow), cd = row_ld_if(ld, crow + LHW);
-                    const float cr_left = (ld && lc.col0 > 0) ? crow[-1] : 0.f;
-                    oBn = row_sel(in, w_core_lin(st.sB1, u, d, l, rr, cr, cr_left, cd, st.cDp), oBn);
-                    st.cDp = cd;
+                        for (int e = 0; e < 4; ++e) w[e] = row_ld(wrow(SM::PL_WL + e, r));
+                        lA[N] = w_L(sA[C], sA[U], sA[N], l, rr, w);
+                    }
+                    nb_lr<false, XW && FINE>(sB[C], l, rr, lc, PL_SB);
+                    const float* crow = wrow(SM::PL_C, r);
+                    const Row cr = row_ld(crow), cd = row_ld(wrow(SM::PL_C + 1, r));
+                    const float cr_left = lc.first ? 0.f : crow[-1];
+                    oB[N] = w_core_lin(sB[C], sB[U], sB[N], l, rr, cr, cr_left, cd, cDp);
+                    cDp = cd;
                     if (THR) {
+                        // raw weights: plane U of this row was read one step ago (it is staged one row ahead), plane D of
+                        // the row above is last step's own[3]
                         RawW rw;
-                        if (ld) {
-                            ld_raw_w(L.wT, L.H, L.W, r, lc.col0, rw);
-                        } else {
+                        rw.own[0] = wU_next;
+                        rw.in[0] = wD_prev;
+                        const float* pL = wrow(SM::PL_WT + 1, r);
+                        const float* pR = wrow(SM::PL_WT + 2, r);
+                        rw.own[1] = row_ld(pL);
+                        rw.own[2] = row_ld(pR);
+                        rw.own[3] = row_ld(wrow(SM::PL_WT + 3, r));
+                        rw.in[3] = r + 1 < L.H ? row_ld(wrow(SM::PL_WT + 0, r + 1)) : row_zero();   // edge U of the lower neighbour
+                        const float wr_m1 = lc.first ? 0.f : pR[-1];                       // edge R of the left neighbour
+                        const float wl_p4 = lc.last ? 0.f : pL[4];                         // edge L of the right neighbour
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) rw.own[e] = rw.in[e] = row_zero();
+                        for (int j = 0; j < 4; ++j) {
+                            rw.in[1].v[j] = j == 0 ? wr_m1 : rw.own[2].v[j - 1];
+                            rw.in[2].v[j] = j == 3 ? wl_p4 : rw.own[1].v[j + 1];
                         }
-                        oTn = row_sel(in, w_core_thr(st.sB1, u, d, l, rr, rw, L.Gam), oTn);
+                        oT[N] = w_core_thr(sB[C], sB[U], sB[N], l, rr, rw, L.Gam);
+                        wU_next = rw.in[3];
+                        wD_prev = rw.own[3];
+                    }
+                } else {
+                    if (GLR) lA[N] = row_zero();
+                    oB[N] = row_zero();
+                    cDp = row_zero();
+                    if (THR) {
+                        oT[N] = row_zero();
+                        wD_prev = row_zero();
+                        wU_next = (r + 1 >= 0 && r + 1 < L.H) ? row_ld(wrow(SM::PL_WT + 0, r + 1)) : row_zero();
                     }
                 }
-                if (GLR) mb_post<XW>(lAn, lc, PL_LA);
-                mb_post<XW>(oBn, lc, PL_OB);
-                if (THR) mb_post<XW>(oTn, lc, PL_OT);
+                if (GLR) mb_post<XW && FINE>(lA[N], lc, PL_LA);
+                mb_post<XW && FINE>(oB[N], lc, PL_OB);
+                if (THR) mb_post<XW && FINE>(oT[N], lc, PL_OT);
             }
             // ---- St at row t-3 and the row's destination
             {
                 const int r = t - 3;
-                float l, rr;
-                nb_lr<true, XW>(st.oB1, l, rr, lc, PL_OB);
-                Row Az = w_St(L.kT, st.oB1, st.oB2, oBn, l, rr);
+                if (FINE ? (r >= R0 && r < R1) : (r >= 0 && r < L.H)) {
+                    float l, rr;
+                    nb_lr<true, XW && FINE>(oB[C], l, rr, lc, PL_OB);
+                    Row Az = w_St(L.kT, oB[C], oB[U], oB[N], l, rr);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) Az.v[j] *= L.aT;
-                if (GLR) {
-                    nb_lr<true, XW>(st.lA1, l, rr, lc, PL_LA);
-                    const Row gl_ = w_St(L.kL, st.lA1, st.lA2, lAn, l, rr);
+                    for (int j = 0; j < 4; ++j) Az.v[j] *= L.aT;
+                    if (GLR) {
+                        nb_lr<true, XW && FINE>(lA[C], l, rr, lc, PL_LA);
+                        const Row gl_ = w_St(L.kL, lA[C], lA[U], lA[N], l, rr);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) Az.v[j] += L.aL * gl_.v[j];
-                }
-                Row rT = row_zero();
-                if (THR) {
-                    nb_lr<true, XW>(st.oT1, l, rr, lc, PL_OT);
-                    rT = w_St(L.kT, st.oT1, st.oT2, oTn, l, rr);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) rT.v[j] *= L.aT;
-                }
-                if (!fine) {
-                    // coarse: hand 0.25 * (coarse term) to the fine epilogue of rows 2r, 2r+1
-                    if (lc.active && r >= 0 && r < L.H) {
-                        float* slot = ring + (size_t)(r & 1) * NRING * ringW + lc.col0;
-                        float v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = 0.25f * Az.v[j];
-                        st4(slot, v);
-                        if (THR) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) v[j] = 0.25f * rT.v[j];
-                            st4(slot + ringW, v);
-                        }
+                        for (int j = 0; j < 4; ++j) Az.v[j] += L.aL * gl_.v[j];
                     }
-                } else if (lc.active && r >= R0 && r < R1) {
-                    const float* slot = ring + (size_t)((r >> 1) & 1) * NRING * ringW + (lc.col0 >> 1);
-                    const float2 cz = *reinterpret_cast<const float2*>(slot);
-                    const Row zq = st.z3;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) Az.v[j] += zq.v[j] + (j < 2 ? cz.x : cz.y);
+                    Row rT = row_zero();
                     if (THR) {
-                        const float2 ct = *reinterpret_cast<const float2*>(slot + ringW);
+                        nb_lr<true, XW && FINE>(oT[C], l, rr, lc, PL_OT);
+                        rT = w_St(L.kT, oT[C], oT[U], oT[N], l, rr);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) rT.v[j] += (j < 2 ? ct.x : ct.y);
+                        for (int j = 0; j < 4; ++j) rT.v[j] *= L.aT;
                     }
-                    const size_t gi = off + (size_t)r * W + lc.col0;
-                    Row in0 = row_zero(), in1 = row_zero(), in2 = row_zero(), o0, o1, o2;
-                    if (MODE == MODE_X2 || has_skip) in0 = row_ld(a.y + gi);
-                    if (MODE == MODE_X3) { in1 = row_ld(a.bB_in + gi); in2 = row_ld(a.r1_in + gi); }
+                    if (!FINE) {
+                        // coarse: hand 0.25 * (coarse term) to the fine epilogue of rows 2r, 2r+1
+                        if (lc.active) {
+                            float* slot = cring + (r & 1) * NRING * Wpc + lc.col0;
+                            float v[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (MODE == MODE_BA) {
-                            o0.v[j] = Az.v[j];  // y + R_lin(y)
-                        } else if (MODE == MODE_X1) {
-                            o0.v[j] = zq.v[j] + alpha * (zq.v[j] - Az.v[j]);
-                        } else if (MODE == MODE_X2) {
-                            const float bB = in0.v[j] + rT.v[j], r1v = bB - Az.v[j];
-                            o1.v[j] = bB;
-                            o2.v[j] = r1v;
-                            o0.v[j] = zq.v[j] + alpha * r1v;
-                        } else {
-                            const float u2 = (in1.v[j] - Az.v[j]) + beta2 * in2.v[j];
-                            const float x3 = zq.v[j] + alpha * u2;
-                            o0.v[j] = has_skip ? s0 * in0.v[j] + s1 * x3 : x3;
+                            for (int j = 0; j < 4; ++j) v[j] = 0.25f * Az.v[j];
+                            st4(slot, v);
+                            if (THR) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v[j] = 0.25f * rT.v[j];
+                                st4(slot + Wpc, v);
+                            }
+                        }
+                    } else {
+                        const float* slot = cring + ((r >> 1) & 1) * NRING * Wpc + (lc.col0 >> 1);
+                        const float2 cz = *reinterpret_cast<const float2*>(slot);
+                        const Row zq = row_ld(zring + zqs * Wp + lc.col0);      // row t-3 is still in the ring
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) Az.v[j] += zq.v[j] + (j < 2 ? cz.x : cz.y);
+                        if (THR) {
+                            const float2 ctv = *reinterpret_cast<const float2*>(slot + Wpc);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) rT.v[j] += (j < 2 ? ctv.x : ctv.y);
+                        }
+                        const float* ops = opring + (r & (STREAM_OPR - 1)) * Wp + lc.col0;
+                        Row in0 = row_zero(), in1 = row_zero(), in2 = row_zero(), o0, o1, o2;
+                        if (MODE == MODE_X2 || has_skip) in0 = row_ld(ops);
+                        if (MODE == MODE_X3) { in1 = row_ld(ops + STREAM_OPR * Wp); in2 = row_ld(ops + 2 * STREAM_OPR * Wp); }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (MODE == MODE_BA) {
+                                o0.v[j] = Az.v[j];  // y + R_lin(y)
+                            } else if (MODE == MODE_X1) {
+                                o0.v[j] = zq.v[j] + alpha * (zq.v[j] - Az.v[j]);
+                            } else if (MODE == MODE_X2) {
+                                const float bB = in0.v[j] + rT.v[j], r1v = bB - Az.v[j];
+                                o1.v[j] = bB;
+                                o2.v[j] = r1v;
+                                o0.v[j] = zq.v[j] + alpha * r1v;
+                            } else {
+                                const float u2 = (in1.v[j] - Az.v[j]) + beta2 * in2.v[j];
+                                const float x3 = zq.v[j] + alpha * u2;
+                                o0.v[j] = has_skip ? s0 * in0.v[j] + s1 * x3 : x3;
+                            }
+                        }
+                        if (lc.active) {
+                            const size_t gi = off + (size_t)r * W + lc.col0;
+                            st4(a.out0 + gi, o0.v);
+                            if (MODE == MODE_X2) { st4(a.out1 + gi, o1.v); st4(a.out2 + gi, o2.v); }
                         }
                     }
-                    st4(a.out0 + gi, o0.v);
-                    if (MODE == MODE_X2) { st4(a.out1 + gi, o1.v); st4(a.out2 + gi, o2.v); }
                 }
             }
-            // ---- rotate the windows
-            st.z3 = st.z2; st.z2 = st.z1; st.z1 = zn;
-            st.sA2 = st.sA1; st.sA1 = sAn; st.sB2 = st.sB1; st.sB1 = sBn;
-            st.lA2 = st.lA1; st.lA1 = lAn; st.oB2 = st.oB1; st.oB1 = oBn;
-            if (THR) { st.oT2 = st.oT1; st.oT1 = oTn; }
+            // ---- advance the ring slots
+            if (FINE) {
+                zs = zs + 1 == ZR ? 0 : zs + 1;
+                zqs = zqs + 1 == ZR ? 0 : zqs + 1;
+            } else {
+                zs = zs + 2 == ZR ? 0 : zs + 2;
+            }
         }
-        if (XW || (m & 1)) __syncthreads();
     }
-    (void)r1;
+    if (!TMA) cp_async_wait_all();
+}
+
+template <int MODE, bool XW, bool TMA>
+__global__ void __launch_bounds__(STREAM_MAXT, STREAM_MINB) k_stream_fwd(StreamFwdArgs a) {
+    GLR_SMEM_DECL(smem);
+    const int W = a.s.W;
+    const int GL = XW ? 64 : (W <= 32 ? 8 : W <= 64 ? 16 : 32), GLc = GL / 2;
+    const int NTF = (a.nch * GL + 31) & ~31;      // fine threads first, then coarse threads (roles never share a warp)
+    const int NT = (int)blockDim.x, tid = (int)threadIdx.x;
+    // clear the staging memory once (rows outside the image are never copied, and what is read in their place must be
+    // finite), initialise the mbarriers, and make both visible to the TMA unit
+    {
+        StreamSmem<MODE> lay; lay.Wp = 4 * GL; lay.nch = a.nch;
+        const int n4 = (int)(lay.total() / 4);
+        const float z4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = tid; i < n4; i += NT) st4(smem + 4 * i, z4);
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < STREAM_NBAR; ++k) mbar_init(smem_advance(smem_addr(smem), (int)lay.bars() + 2 * k), 1);
+        }
+        mbar_fence_init();
+        __syncthreads();
+    }
+    if (tid < NTF) stream_walk<MODE, XW, true, TMA>(a, smem, tid / GL, NTF / GL, tid % GL, GL);
+    else stream_walk<MODE, XW, false, TMA>(a, smem, (tid - NTF) / GLc, (NT - NTF) / GLc, (tid - NTF) % GLc, GL);
 }
 
 // symmetric GTV coefficients of one weight set: c[0] = wR^2 + wL[.,w+1]^2, c[1] = wD^2 + wU[h+1,.]^2 (0 for the missing neighbour)
@@ -325,16 +634,15 @@ int glr_stream_eligible(const glrgtv_shape* s) {
 
 struct StreamPlan {
     int GL, nch, threads, band_rows, n_bands;
-    size_t smem;
 };
-static StreamPlan stream_plan(const glrgtv_shape& s, int nring) {
+static StreamPlan stream_plan(const glrgtv_shape& s) {
     StreamPlan p;
     p.GL = s.W > 128 ? 64 : s.W > 64 ? 32 : s.W > 32 ? 16 : 8;
     p.nch = 1;
     for (int n = 1; n <= s.F; ++n) {
         if (s.F % n) continue;
         const int thr = ((n * p.GL + 31) & ~31) + ((n * p.GL / 2 + 31) & ~31);
-        if (thr <= 320) p.nch = n;
+        if (thr <= STREAM_MAXT) p.nch = n;
     }
     p.threads = ((p.nch * p.GL + 31) & ~31) + ((p.nch * p.GL / 2 + 31) & ~31);
     // whole-height bands unless the grid would leave SMs idle
@@ -343,22 +651,50 @@ static StreamPlan stream_plan(const glrgtv_shape& s, int nring) {
     while (ctas * bands < 296 && s.H / (bands * 2) >= 32) bands *= 2;
     p.band_rows = ((s.H + bands - 1) / bands + 1) & ~1;
     p.n_bands = (s.H + p.band_rows - 1) / p.band_rows;
-    p.smem = ((size_t)p.nch * 2 * nring * 2 * p.GL + (size_t)2 * p.nch * PL_COUNT * 2 + 8) * sizeof(float);
     return p;
 }
 
+// 0: automatic (measured on B200: the TMA producer wins for the thresholded stage X2, whose CTA stages ten weight planes
+// per level; the per-thread cp.async loader wins for the other three), 1: cp.async everywhere, 2: TMA everywhere
+int g_glr_stream_loader = 0;
+extern "C" int glrgtv_set_stream_loader(int mode) {
+    if (mode < 0 || mode > 2) return GLRGTV_ERR_UNSUPPORTED;
+    g_glr_stream_loader = mode;
+    return GLRGTV_OK;
+}
+
+template <int MODE, bool XW, bool TMA>
+static int launch_stream_kernel(const StreamFwdArgs& a, const StreamPlan& p, long blocks, void* stream) {
+    StreamSmem<MODE> lay; lay.Wp = 4 * p.GL; lay.nch = p.nch;
+    const size_t smem = lay.total() * sizeof(float);
+    if (smem > 227 * 1024) return GLRGTV_ERR_UNSUPPORTED;
+#ifndef GLRGTV_EMU
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(k_stream_fwd<MODE, XW, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return glr_record_launch_error();
+        configured = smem;
+    }
+#endif
+    GLR_LAUNCH_FIBERS((k_stream_fwd<MODE, XW, TMA>), dim3((unsigned)blocks), p.threads, smem, stream, a);
+    return GLRGTV_OK;
+}
 template <int MODE>
 static int launch_stream_stage(StreamFwdArgs a, void* stream) {
     const glrgtv_shape& s = a.s;
-    const StreamPlan p = stream_plan(s, MODE == MODE_X2 ? 2 : 1);
+    const StreamPlan p = stream_plan(s);
     a.nch = p.nch; a.band_rows = p.band_rows; a.n_bands = p.n_bands;
     const long blocks = (long)s.B * s.G * (s.F / p.nch) * p.n_bands;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
     GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_BA + MODE, stream);
-    if (p.GL == 64) GLR_LAUNCH_FIBERS((k_stream_fwd<MODE, true>), dim3((unsigned)blocks), p.threads, p.smem, stream, a);
-    else GLR_LAUNCH_FIBERS((k_stream_fwd<MODE, false>), dim3((unsigned)blocks), p.threads, p.smem, stream, a);
+    // the TMA producer keeps at most 32 * STREAM_MAXI row copies per batch
+    const int nf = StreamSmem<MODE>::NPL + p.nch * StreamSmem<MODE>::NOP, nc = StreamSmem<MODE>::NPL + 2 * p.nch;
+    const bool want_tma = g_glr_stream_loader == 2 || (g_glr_stream_loader == 0 && MODE == MODE_X2);
+    const bool tma = want_tma && 2 * nf + nc <= 32 * STREAM_MAXI;
+    const int rc = p.GL == 64 ? (tma ? launch_stream_kernel<MODE, true, true>(a, p, blocks, stream) : launch_stream_kernel<MODE, true, false>(a, p, blocks, stream))
+                              : (tma ? launch_stream_kernel<MODE, false, true>(a, p, blocks, stream) : launch_stream_kernel<MODE, false, false>(a, p, blocks, stream));
     GLR_PROF_END(GLRGTV_SLOT_FWD_BA + MODE, stream);
-    return GLR_CHECK_LAUNCH();
+    return rc ? rc : GLR_CHECK_LAUNCH();
 }
 
 int glr_launch_gtv_coeffs(const glrgtv_shape& s, const float* w, float* c, void* stream) {

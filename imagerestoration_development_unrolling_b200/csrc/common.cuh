@@ -23,6 +23,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 struct emu_dim3 {
@@ -56,6 +57,7 @@ static inline float __shfl_xor_sync(unsigned, float v, int m, int width = 32) {
     const int lane = (int)(threadIdx.x & 31u);
     return emu_shfl(v, lane ^ m);
 }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline float __ldg(const float* p) { return *p; }
 typedef void* cudaStream_t;
@@ -115,6 +117,8 @@ static inline int glr_memset_async(void* p, int v, size_t n, cudaStream_t s) {
 
 // ------------------------------------------------------------------ small device helpers
 __host__ __device__ __forceinline__ int glr_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__host__ __device__ __forceinline__ int glr_maxi(int a, int b) { return a > b ? a : b; }
+__host__ __device__ __forceinline__ int glr_mini(int a, int b) { return a < b ? a : b; }
 __host__ __device__ __forceinline__ int glr_reflecti(int v, int n) {
     // torch 'reflect' padding by one pixel: -1 -> 1, n -> n-2
     if (v < 0) v = -v;

@@ -141,3 +141,52 @@ __device__ __forceinline__ Row w_core_thr(const Row& c, const Row& u, const Row&
     }
     return o;
 }
+
+// ------------------------------------------------------------------ TMA bulk copies + mbarrier (sm_90+ / sm_100a)
+// One elected thread moves whole image rows global -> shared with cp.async.bulk (the TMA unit; SASS: UBLKCP) and the
+// bytes are counted on an mbarrier that every consumer polls.  The emulation build copies synchronously.
+#ifdef GLRGTV_EMU
+typedef float* smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(float* p) { return p; }
+__device__ __forceinline__ void mbar_init(smem_addr_t, unsigned) {}
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void mbar_expect_tx(smem_addr_t, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(smem_addr_t dst, const float* src, unsigned bytes, smem_addr_t) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(smem_addr_t, unsigned) {}
+__device__ __forceinline__ smem_addr_t smem_advance(smem_addr_t a, int floats) { return a + floats; }
+__device__ __forceinline__ void cp_async16_s(smem_addr_t dst, const float* src) { for (int j = 0; j < 4; ++j) dst[j] = src[j]; }
+#else
+typedef unsigned smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(float* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ smem_addr_t smem_advance(smem_addr_t a, int floats) { return a + 4u * (unsigned)floats; }
+// 16-byte cp.async with a precomputed shared-window address
+__device__ __forceinline__ void cp_async16_s(smem_addr_t dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void mbar_init(smem_addr_t bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+// make the barrier initialisation (and earlier generic-proxy writes to shared memory) visible to the async proxy
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(smem_addr_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(smem_addr_t dst, const float* src, unsigned bytes, smem_addr_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(smem_addr_t bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+#endif

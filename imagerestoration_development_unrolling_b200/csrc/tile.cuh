@@ -300,6 +300,7 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src) { for (
 __device__ __forceinline__ void cp_async4(float* dst, const float* src) { *dst = *src; }
 __device__ __forceinline__ void cp_async_commit() {}
 __device__ __forceinline__ void cp_async_wait_all() {}
+template <int N> __device__ __forceinline__ void cp_async_wait_pending() {}
 #else
 __device__ __forceinline__ void cp_async16(float* dst, const float* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
@@ -309,6 +310,8 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// wait until at most N of this thread's most recent commit groups are still in flight
+template <int N> __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif
 
 // issue (do not wait for) the copy of one channel plane's (+)6 region into `raw`

@@ -14,11 +14,13 @@ CASES = [(12, 2, 2, 12, 16), (6, 1, 1, 10, 8), (12, 2, 1, 20, 24), (12, 4, 1, 14
          (6, 1, 1, 12, 72), (6, 2, 1, 6, 128), (3, 1, 1, 8, 136), (2, 1, 1, 6, 256), (24, 2, 1, 2, 8)]
 
 
-@pytest.fixture(autouse=True)
-def stream_path():
+@pytest.fixture(autouse=True, params=[1, 2], ids=["cp_async", "tma"])
+def stream_path(request):
     E.emu_lib().glrgtv_set_block_path(2)
+    E.emu_lib().glrgtv_set_stream_loader(request.param)
     yield
     E.emu_lib().glrgtv_set_block_path(0)
+    E.emu_lib().glrgtv_set_stream_loader(0)
 
 
 @pytest.mark.parametrize("case", CASES)
