@@ -18,6 +18,7 @@
 // Upstream gradients that are pointwise functions of (gout, gx2) are rebuilt on the fly instead of being
 // stored:  gr2 = a2 s1 gout,  gr1 = b2 gr2 + a1 gx2,  gbB = gr2 + gr1.
 #include "tile.cuh"
+#include "stream_bwd.cuh"
 
 enum { BWD_X3 = 0, BWD_X2 = 1, BWD_X1 = 2, BWD_BA = 3 };
 
@@ -760,6 +761,12 @@ extern "C" size_t glrgtv_block_bwd_workspace_bytes(const glrgtv_shape* s) {
 }
 
 int glr_block_params_ok(const glrgtv_shape* s, const glrgtv_block_params* p);
+// block_stream_fwd.cu
+extern int g_glr_block_path;
+int glr_stream_eligible(const glrgtv_shape* s);
+#ifndef GLR_STREAM_BWD_MIN_W
+#define GLR_STREAM_BWD_MIN_W 8      // narrower planes take the plane kernels in automatic mode
+#endif
 
 extern "C" int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params* p, const float* x,
                                 const float* feat0, const float* feat1, const glrgtv_block_saved* sv,
@@ -785,6 +792,50 @@ extern "C" int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params
 
     float* ws = (float*)workspace;
     const size_t N = (size_t)s->B * s->H * s->W, GE = (size_t)s->G * 4;
+    // register-streaming backward (block_stream_bwd.cu + block_gw.cu) where the shape allows, else the plane kernels
+    const bool can_stream = glr_stream_eligible(s) && sv->cT0 && sv->cT1;
+    if (g_glr_block_path == 2 && !can_stream) return GLRGTV_ERR_UNSUPPORTED;
+    if (can_stream && g_glr_block_path != 1 && (g_glr_block_path == 2 || s->W >= GLR_STREAM_BWD_MIN_W)) {
+        StreamBwdArgs b;
+        b.s = *s; b.p = *p; b.gr = *gr;
+        b.wT0 = sv->wT0; b.wL0 = sv->wL0; b.wT1 = sv->wT1; b.wL1 = sv->wL1; b.cT0 = sv->cT0; b.cT1 = sv->cT1;
+        b.nch = 1; b.band_rows = s->H; b.n_bands = 1;
+        GwArgs w;
+        w.s = *s; w.p = *p; w.ggamma0 = gr->gamma0; w.ggamma1 = gr->gamma1; w.wT0 = sv->wT0; w.wT1 = sv->wT1;
+        w.gwT0 = ws + o_gw; w.gwL0 = w.gwT0 + GE * N; w.gwT1 = w.gwL0 + GE * N; w.gwL1 = w.gwT1 + GE * (N / 4);
+        float *gx2 = ws + o_gx2, *gx1 = ws + o_gx1, *gbA = ws + o_gbA;
+        // X3: through x3 = x2 + a2 (r2 + b2 r1), r2 = bB - A x2
+        b.z = sv->x2; b.src0 = gout; b.src1 = nullptr; b.op0 = sv->r1; b.op1 = sv->bB; b.op2 = x; b.out = gx2;
+        if ((rc = glr_stream_bwd_stage<BW_X3>(b, GLRGTV_SLOT_BWD_X3, stream))) return rc;
+        w.z = sv->x2; w.src0 = gout; w.src1 = nullptr; w.assign = 1;
+        if ((rc = glr_gw_stage<BW_X3>(w, GLRGTV_SLOT_BWD_X3, stream))) return rc;
+        // X2: through x2 = x1 + a1 r1, r1 = bB - A x1 (part A) and bB = y + R_thr x1 (part B)
+        b.z = sv->x1; b.src0 = gout; b.src1 = gx2; b.op0 = sv->r1; b.op1 = nullptr; b.op2 = nullptr; b.out = gx1;
+        if ((rc = glr_stream_bwd_stage<BW_X2A>(b, GLRGTV_SLOT_BWD_X2, stream))) return rc;
+        b.op0 = gx1;
+        if ((rc = glr_stream_bwd_stage<BW_X2B>(b, GLRGTV_SLOT_BWD_X2, stream))) return rc;
+        w.z = sv->x1; w.src0 = gout; w.src1 = gx2; w.assign = 0;
+        if ((rc = glr_gw_stage<BW_X2A>(w, GLRGTV_SLOT_BWD_X2, stream))) return rc;      // both parts of X2 in one pass
+        // X1: through x1 = bA + a0 (bA - A bA)
+        b.z = sv->bA; b.src0 = gx1; b.src1 = nullptr; b.op0 = nullptr; b.out = gbA;
+        if ((rc = glr_stream_bwd_stage<BW_X1>(b, GLRGTV_SLOT_BWD_X1, stream))) return rc;
+        w.z = sv->bA; w.src0 = gx1; w.src1 = nullptr;
+        if ((rc = glr_gw_stage<BW_X1>(w, GLRGTV_SLOT_BWD_X1, stream))) return rc;
+        // BA: through bA = y + R_lin y, plus the pointwise paths into y (bB, skip)
+        b.z = x; b.src0 = gbA; b.op0 = gout; b.op1 = gx2; b.out = gx;
+        if ((rc = glr_stream_bwd_stage<BW_BA>(b, GLRGTV_SLOT_BWD_BA, stream))) return rc;
+        w.z = x; w.src0 = gbA;
+        if ((rc = glr_gw_stage<BW_BA>(w, GLRGTV_SLOT_BWD_BA, stream))) return rc;
+        glrgtv_shape sc = *s;
+        sc.H /= 2; sc.W /= 2;
+        GLR_PROF_BEGIN(GLRGTV_SLOT_BWD_WEIGHTS, stream);
+        if ((rc = glr_block_weights_bwd(s, feat0, p->gtv0.multiM, p->glr0.multiM, sv->wT0, sv->wL0, w.gwT0, w.gwL0, gfeat0,
+                                        gr->gtv0_M, gr->glr0_M, stream))) return rc;
+        rc = glr_block_weights_bwd(&sc, feat1, p->gtv1.multiM, p->glr1.multiM, sv->wT1, sv->wL1, w.gwT1, w.gwL1, gfeat1,
+                                   gr->gtv1_M, gr->glr1_M, stream);
+        GLR_PROF_END(GLRGTV_SLOT_BWD_WEIGHTS, stream);
+        return rc;
+    }
     BlockBwdArgs a;
     a.s = *s; a.p = *p; a.gr = *gr;
     a.wT0 = sv->wT0; a.wL0 = sv->wL0; a.wT1 = sv->wT1; a.wL1 = sv->wL1;

@@ -621,6 +621,8 @@ __global__ void __launch_bounds__(256) k_gtv_coeffs(int planes, int H, int W, co
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+unsigned long long g_glr_stream_launches = 0;   // streaming-path kernels launched (diagnostic)
+extern "C" unsigned long long glrgtv_stream_launch_count(void) { return g_glr_stream_launches; }
 int g_glr_block_path = 0;   // 0 auto, 1 plane kernels only, 2 streaming kernels (error when the shape is not eligible)
 extern "C" int glrgtv_set_block_path(int mode) {
     if (mode < 0 || mode > 2) return GLRGTV_ERR_UNSUPPORTED;
@@ -676,6 +678,7 @@ static int launch_stream_kernel(const StreamFwdArgs& a, const StreamPlan& p, lon
         configured = smem;
     }
 #endif
+    ++g_glr_stream_launches;
     GLR_LAUNCH_FIBERS((k_stream_fwd<MODE, XW, TMA>), dim3((unsigned)blocks), p.threads, smem, stream, a);
     return GLRGTV_OK;
 }

@@ -162,9 +162,9 @@ __device__ __forceinline__ StatsTaps glr_load_taps(const glrgtv_stats& st, int c
 // block-wide sum; result valid in thread 0 (emu: single thread).  `red` = >= 32 floats of shared memory.
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #ifdef GLRGTV_EMU
-    (void)red;
-    return v;
-#else
+    if (!emu_fiber_mode) { (void)red; return v; }
+#endif
+    {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -172,13 +172,13 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     if (lane == 0) red[wid] = v;
     __syncthreads();
     int nw = (blockDim.x + 31) >> 5;
-    v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+    v = ((int)threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
     if (wid == 0) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     }
     return v;
-#endif
+    }
 }
 
 static inline int glr_shape_ok(const glrgtv_shape* s) {

@@ -208,6 +208,8 @@ int glrgtv_set_block_path(int mode);
 /* Loader of the streaming kernels: 0 = automatic (per stage, as measured), 1 = per-thread cp.async rings,
  * 2 = one producer warp issuing TMA bulk row copies (cp.async.bulk + mbarrier).  Same results; a tuning switch. */
 int glrgtv_set_stream_loader(int mode);
+/* streaming-path kernels launched since the library was loaded (diagnostic: lets a test assert which path ran) */
+unsigned long long glrgtv_stream_launch_count(void);
 
 /* x [B,C,H,W]; feat0 = patchs_features_extraction00(x) [B,2C,H,W]; feat1 = ..01(x) [B,2C,H/2,W/2]
  * (first C channels feed GTV, last C feed GLR, V1X0:714, 726);  out [B,C,H,W]. */

@@ -43,3 +43,39 @@ def test_stream_block_forward(case):
     for n in ("bA", "x1", "bB", "r1", "x2"):
         assert rel(saved[n], inter[n]) < 2e-5, (n, rel(saved[n], inter[n]))
     assert rel(out, ref_out) < 1e-5
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_stream_block_backward(case):
+    dim, G, B, H, W = case
+    F = dim // G
+    sd = random_block_state(dim, G, seed=400 + H)
+    gen = torch.Generator().manual_seed(H * W + 1)
+    x = torch.randn(B, dim, H, W, generator=gen)
+    gout = torch.randn(B, dim, H, W, generator=gen)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    _, gx_ref, pg_ref = O.lowpass_block_fwd_bwd(sd64, x.double(), gout.double())
+    xx = x.clone().requires_grad_(True)
+    pw = {k: sd[k].clone().requires_grad_(True) for k in sd if "patchs_features_extraction" in k}
+    f0, f1 = oracle_features({**sd, **pw}, xx)
+    p, keep = block_structs(sd)
+    sv, saved = alloc_saved(B, G, F, H, W)
+    out = torch.empty_like(x)
+    shp = L.make_shape(B, G, F, H, W)
+    E.call("glrgtv_block_fwd", shp, p, x, f0.detach(), f1.detach(), out, sv, None)
+    gr, gkeep = alloc_grads(G, F)
+    nbytes = E.emu_lib().glrgtv_block_bwd_workspace_bytes(shp)
+    ws = torch.empty(nbytes // 4)
+    gx, gf0, gf1 = torch.empty_like(x), torch.empty_like(f0), torch.empty_like(f1)
+    n0 = E.emu_lib().glrgtv_stream_launch_count()
+    E.call("glrgtv_block_bwd", shp, p, x, f0.detach(), f1.detach(), sv, gout, gx, gf0, gf1, gr, ws, nbytes, None)
+    assert E.emu_lib().glrgtv_stream_launch_count() - n0 == 13      # 5 stage kernels + 4 x 2 edge-weight-gradient kernels
+    names = list(pw)
+    gfeat = torch.autograd.grad([f0, f1], [xx] + [pw[k] for k in names], [gf0, gf1])
+    gx_total = gx + gfeat[0]
+    got = grads_to_state_names(gkeep, G, F)
+    got.update({k: g for k, g in zip(names, gfeat[1:])})
+    errs = {k: (rel(got[k], ref) if float(ref.abs().max()) > 0 else float(got[k].abs().max())) for k, ref in pg_ref.items()}
+    errs["gx"] = rel(gx_total, gx_ref)
+    bad = {k: v for k, v in errs.items() if v > 2e-4}
+    assert not bad, bad
