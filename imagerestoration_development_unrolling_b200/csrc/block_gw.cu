@@ -106,24 +106,34 @@ __global__ void __launch_bounds__(GW_NT) k_gw_stage(GwArgs a) {
     // operand at this resolution: the tensor itself, or its 2x2 mean
     auto ld = [&](const float* q) -> float { return COARSE ? 0.25f * (q[0] + q[1] + q[W] + q[W + 1]) : q[0]; };
 
+    // operands of one channel for this thread's tile elements, fetched one channel ahead of their use
+    float vz[GW_NZ], v0[GW_NZ], v1[GW_NZ];
+    auto fetch = [&](int f) {
+        const size_t off = ((size_t)b * G * F + (size_t)g * F + f) * HW;
+#pragma unroll
+        for (int k = 0; k < GW_NZ; ++k) {
+            vz[k] = v0[k] = v1[k] = 0.f;
+            if (zoff[k] < 0) continue;
+            vz[k] = ld(a.z + off + zoff[k]);
+            if (zin[k]) {
+                v0[k] = ld(a.src0 + off + zoff[k]);
+                if (X2) v1[k] = ld(a.src1 + off + zoff[k]);
+            }
+        }
+    };
+    fetch(0);
     for (int f = 0; f < F; ++f) {
         const int c = g * F + f;
-        const size_t off = ((size_t)b * G * F + c) * HW;
         const StatsTaps kT = glr_load_taps(stT, c), kL = HAS_L ? glr_load_taps(stL, c) : kT;
 #pragma unroll
         for (int k = 0; k < GW_NZ; ++k) {
             if (zoff[k] < 0) continue;
             const int i = (int)threadIdx.x + k * GW_NT;
-            zt[i] = ld(a.z + off + zoff[k]);
-            float gv = 0.f, gv2 = 0.f;
-            if (zin[k]) {
-                const float q0 = ld(a.src0 + off + zoff[k]);
-                gv = ca * q0;
-                if (X2) { const float q1 = ld(a.src1 + off + zoff[k]); gv += cb * q1; gv2 = ca2 * q0 + cb2 * q1; }
-            }
-            gt[i] = gv;
-            if (X2) g2[i] = gv2;
+            zt[i] = vz[k];
+            gt[i] = ca * v0[k] + cb * v1[k];
+            if (X2) g2[i] = ca2 * v0[k] + cb2 * v1[k];
         }
+        if (f + 1 < F) fetch(f + 1);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < GW_NS; ++k) {

@@ -588,9 +588,15 @@ static BwPlan bw_plan(const glrgtv_shape& s) {
         const int nf = (n * p.GL + 31) & ~31, nc = (n * p.GL / 2 + 31) & ~31;
         return (HAS_L ? 2 : 1) * (nf + nc);
     };
+    // channels per CTA: as many as the thread budget and shared memory allow (measured on B200: sharing the staged
+    // weight rows between more channel walkers beats the extra resident CTAs of a smaller choice)
     p.nch = 1;
-    for (int n = 1; n <= s.F; ++n)
-        if (s.F % n == 0 && threads(n) <= BW_MAXT) p.nch = n;
+    for (int n = 1; n <= s.F; ++n) {
+        if (s.F % n || threads(n) > BW_MAXT) continue;
+        BwSmem<MODE> lay; lay.Wp = 4 * p.GL; lay.nch = n;
+        if (lay.total() * sizeof(float) + 1024 > 227 * 1024) continue;
+        p.nch = n;
+    }
     p.threads = threads(p.nch);
     const long ctas = (long)s.B * s.G * (s.F / p.nch);
     int bands = 1;
