@@ -62,6 +62,9 @@ struct Lvl {
 #define STREAM_OPR 4
 #define STREAM_WR 4
 #define STREAM_NBAR 4
+#ifndef STREAM_PHASES
+#define STREAM_PHASES 0   // 0: per stage (see stream_walk), 1: rotated windows everywhere, 3: phase-unrolled everywhere
+#endif
 #define STREAM_PD 2      // cp.async loader: block steps between issuing a copy and reading it
 #define STREAM_MAXJ 5    // cp.async loader: weight-plane copies per thread and step held as precomputed descriptors
 template <int MODE>
@@ -166,7 +169,7 @@ __device__ __forceinline__ ProdItem stream_item(const StreamFwdArgs& a, const St
         return p;
     }
     if (NOP > 0) {                                       // epilogue operands of row t-3, per channel
-        const int ch = idx / NOP, k = idx - ch * NOP;
+        const int ch = idx / (NOP > 0 ? NOP : 1), k = idx - ch * NOP;
         if (MODE == MODE_X3 && k == 0 && !has_skip) return p;
         p.src0 = (k == 0 ? a.y : k == 1 ? a.bB_in : a.r1_in) + off0 + (size_t)ch * HW;
         p.r_off = t_off - 3;
@@ -369,11 +372,18 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
         if (producer) { stream_produce(items, smem, (int)lay.bars(), 0, pw_lane); stream_produce(items, smem, (int)lay.bars(), 1, pw_lane); }
     }
 
-    for (int m0 = 0; m0 < M; m0 += 6) {
+    // PH3: the step is unrolled over the three window phases (no register moves, 6x the code); otherwise one step body
+    // whose windows are rotated with register moves.  The 32 KB L1.5 instruction cache decides: measured on B200, the
+    // thresholded stage X2 (the largest body) is faster rotated, the other three are faster unrolled.
+    constexpr bool PH3 = STREAM_PHASES == 3 || (STREAM_PHASES == 0 && MODE != MODE_X2);
+    constexpr int KU = PH3 ? 6 : 1;
+#pragma unroll 1
+    for (int m0 = 0; m0 < M; m0 += KU) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const int m = m0 + k;
+        for (int ku = 0; ku < KU; ++ku) {
+            const int m = m0 + ku;
             if (m >= M) break;
+            const int k = PH3 ? ku : (m & 1);
             if (TMA) {
                 const int j = (m + 1) >> 1;
                 mbar_wait(smem_advance(bars, 2 * (j & (STREAM_NBAR - 1))), (unsigned)(j >> 2) & 1u);
@@ -388,7 +398,7 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
             }
             if (FINE && m < STREAM_DF) continue;
             // window phase: the new row goes to slot N, the centre row (new one step ago) is C, the upper row is U
-            const int N = FINE ? k % 3 : k / 2, C = (N + 2) % 3, U = (N + 1) % 3;
+            const int N = PH3 ? (FINE ? ku % 3 : ku / 2) : 2, C = PH3 ? (N + 2) % 3 : 1, U = PH3 ? (N + 1) % 3 : 0;
             const int t = r0 - 3 + (FINE ? m - STREAM_DF : (m >> 1));     // newest row of this step
             if (XW && FINE) {
                 lc.mb_rd = mbox + ((m + 1) & 1) * nch * PL_COUNT * 2 + wk * PL_COUNT * 2;
@@ -567,6 +577,11 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
             } else {
                 zs = zs + 2 == ZR ? 0 : zs + 2;
             }
+            if (!PH3) {
+                z[U] = z[C]; z[C] = z[N]; sB[U] = sB[C]; sB[C] = sB[N]; oB[U] = oB[C]; oB[C] = oB[N];
+                if (GLR) { sA[U] = sA[C]; sA[C] = sA[N]; lA[U] = lA[C]; lA[C] = lA[N]; }
+                if (THR) { oT[U] = oT[C]; oT[C] = oT[N]; }
+            }
         }
     }
     if (!TMA) cp_async_wait_all();
@@ -656,8 +671,8 @@ static StreamPlan stream_plan(const glrgtv_shape& s) {
     return p;
 }
 
-// 0: automatic (measured on B200: the TMA producer wins for the thresholded stage X2, whose CTA stages ten weight planes
-// per level; the per-thread cp.async loader wins for the other three), 1: cp.async everywhere, 2: TMA everywhere
+// 0: automatic (measured on B200: the TMA producer wins for the thresholded stage X2 - ten weight planes per level - on
+// rows of 512 bytes and more; the per-thread cp.async loader wins elsewhere), 1: cp.async everywhere, 2: TMA everywhere
 int g_glr_stream_loader = 0;
 extern "C" int glrgtv_set_stream_loader(int mode) {
     if (mode < 0 || mode > 2) return GLRGTV_ERR_UNSUPPORTED;
@@ -692,7 +707,7 @@ static int launch_stream_stage(StreamFwdArgs a, void* stream) {
     GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_BA + MODE, stream);
     // the TMA producer keeps at most 32 * STREAM_MAXI row copies per batch
     const int nf = StreamSmem<MODE>::NPL + p.nch * StreamSmem<MODE>::NOP, nc = StreamSmem<MODE>::NPL + 2 * p.nch;
-    const bool want_tma = g_glr_stream_loader == 2 || (g_glr_stream_loader == 0 && MODE == MODE_X2);
+    const bool want_tma = g_glr_stream_loader == 2 || (g_glr_stream_loader == 0 && MODE == MODE_X2 && s.W >= 128);
     const bool tma = want_tma && 2 * nf + nc <= 32 * STREAM_MAXI;
     const int rc = p.GL == 64 ? (tma ? launch_stream_kernel<MODE, true, true>(a, p, blocks, stream) : launch_stream_kernel<MODE, true, false>(a, p, blocks, stream))
                               : (tma ? launch_stream_kernel<MODE, false, true>(a, p, blocks, stream) : launch_stream_kernel<MODE, false, false>(a, p, blocks, stream));
