@@ -147,27 +147,34 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ roofline bookkeeping
-SLOTS = ["fwd_weights", "fwd_BA", "fwd_X1", "fwd_X2", "fwd_X3", "bwd_X3", "bwd_X2", "bwd_X1", "bwd_BA", "bwd_weights"]
+SLOTS = ["fwd_weights", "fwd_BA", "fwd_X1", "fwd_X2", "fwd_X3", "bwd_X3", "bwd_X2", "bwd_X1", "bwd_BA", "bwd_weights",
+         "gw_X3", "gw_X2", "gw_X1", "gw_BA"]
 
 
 def algorithmic_bytes(slot, B):
-    """fp32 bytes one step moves through kernel `slot`, summed over the four scales: every operand tensor read
-    once + every result written once (DESIGN.md 'algorithmic bytes'); halo re-reads are not algorithmic."""
+    """fp32 bytes one step moves through the kernels of `slot`, summed over the four scales: every operand tensor read
+    once + every result written once; halo re-reads and L2 hits are not algorithmic.
+    C = channels, GE = 4G edge-weight planes of one set at full resolution; 1.25 = fine + quarter-size coarse set;
+    the symmetric GTV coefficients cT are half a set (0.625 GE with its coarse part)."""
     total = 0
     for s, (C, G) in enumerate(zip(DIMS, NGRAPHS)):
         N = B * (RES >> s) * (RES >> s)
         GE = 4 * G
         per_px = {
-            "fwd_weights": 1.25 * (2 * C + 2 * GE),
-            "fwd_BA": 2 * C + 1.25 * GE,
-            "fwd_X1": 2 * C + 2.5 * GE,
-            "fwd_X2": 5 * C + 2.5 * GE,
-            "fwd_X3": 5 * C + 2.5 * GE,
-            "bwd_X3": 6 * C + 5 * GE,
-            "bwd_X2": 5 * C + 7.5 * GE,
-            "bwd_X1": 3 * C + 7.5 * GE,
-            "bwd_BA": 5 * C + 3.75 * GE,
+            "fwd_weights": 1.25 * (2 * C + 2 * GE) + 1.875 * GE,        # feat -> wT, wL; wT -> cT
+            "fwd_BA": 2 * C + 0.625 * GE,                               # y, cT -> bA
+            "fwd_X1": 2 * C + 1.875 * GE,                               # bA, wL, cT -> x1
+            "fwd_X2": 5 * C + 3.125 * GE,                               # x1, y, wL, cT, wT -> x2, bB, r1
+            "fwd_X3": 5 * C + 1.875 * GE,                               # x2, bB, r1, x, wL, cT -> out
+            "bwd_X3": 6 * C + 1.875 * GE,                               # gout, x2, bB, r1, x, wL, cT -> gx2
+            "bwd_X2": 10 * C + 3.125 * GE,                              # A: x1, gout, gx2, r1 -> gx1 ; B: x1, gout, gx2, gx1 -> gx1
+            "bwd_X1": 3 * C + 1.875 * GE,                               # bA, gx1, wL, cT -> gbA
+            "bwd_BA": 5 * C + 0.625 * GE,                               # y, gbA, gout, gx2, cT -> gx
             "bwd_weights": 2.5 * (2 * C + 2 * GE),
+            "gw_X3": 2 * C + 1.25 * GE + 2.5 * GE,                      # x2, gout, wT -> gwL, gwT
+            "gw_X2": 3 * C + 1.25 * GE + 5 * GE,                        # x1, gout, gx2, wT, gw -> gw
+            "gw_X1": 2 * C + 1.25 * GE + 5 * GE,
+            "gw_BA": 2 * C + 1.25 * GE + 2.5 * GE,                      # y, gbA, wT, gwT -> gwT
         }[slot]
         total += per_px * N * 4
     return total
@@ -321,10 +328,21 @@ def main():
         peak, peak_src = measured_peaks()
         achieved = algorithmic_bytes(top, B) / (top_ms_per_step / 1e3) / 1e9
         whole_ms = sum(v[0] for v in per_slot.values()) / a.steps
+        # DRAM bytes of the same kernels from the committed ncu capture of one step at these sizes (profiles/, tools/ncu_slots.py)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_step_slots.json")
+        if os.path.exists(tp) and B == BATCH:
+            traffic = json.load(open(tp))["slots"].get(top, {}).get("dram_bytes")
+        per_kernel = {}
+        for k, v in per_slot.items():
+            gbs = algorithmic_bytes(k, B) / (v[0] / a.steps / 1e3) / 1e9
+            per_kernel[k] = {"ms": round(v[0] / a.steps, 4), "launches": int(v[1] // a.steps), "GBs": round(gbs, 1), "frac": round(gbs / peak, 4)}
         roofline = {
             "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_source": peak_src, "traffic": None,
-            "kernel_ms_per_step": {k: round(v[0] / a.steps, 4) for k, v in per_slot.items()},
+            "peak_source": peak_src, "traffic": traffic,
+            "note": "a slot = the launches of one solver stage over the four scales (bwd_X2 = parts A and B); achieved = "
+                    "algorithmic bytes of the slot / its summed CUDA-event time inside the timed region",
+            "per_kernel": per_kernel,
             "kernel_share_of_step": round(top_ms_per_step / (ms / a.steps), 4),
             "own_kernels_share_of_step": round(whole_ms / (ms / a.steps), 4),
             "whole_block_compulsory_GBs": sum(20 * C * B * (RES >> s) ** 2 for s, C in enumerate(DIMS)) / (ms / a.steps / 1e3) / 1e9,

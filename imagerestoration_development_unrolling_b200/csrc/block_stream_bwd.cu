@@ -549,8 +549,12 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
     }
 }
 
+// threads per CTA / resident CTAs the register budget is sized for.  The thresholded stage X2B stages two source tensors
+// and four raw weight planes per level: two of its CTAs do not fit one SM's shared memory, so it runs ONE larger CTA.
+template <int MODE> struct BwLaunch { static constexpr int MAXT = MODE == BW_X2B ? 288 : BW_MAXT, MINB = MODE == BW_X2B ? 1 : 2; };
+
 template <int MODE, bool XW>
-__global__ void __launch_bounds__(BW_MAXT, 2) k_stream_bwd(StreamBwdArgs a) {
+__global__ void __launch_bounds__(BwLaunch<MODE>::MAXT, BwLaunch<MODE>::MINB) k_stream_bwd(StreamBwdArgs a) {
     GLR_SMEM_DECL(smem);
     constexpr bool HAS_L = BwSmem<MODE>::HAS_L;
     const int W = a.s.W;
@@ -592,7 +596,7 @@ static BwPlan bw_plan(const glrgtv_shape& s) {
     // weight rows between more channel walkers beats the extra resident CTAs of a smaller choice)
     p.nch = 1;
     for (int n = 1; n <= s.F; ++n) {
-        if (s.F % n || threads(n) > BW_MAXT) continue;
+        if (s.F % n || threads(n) > BwLaunch<MODE>::MAXT) continue;
         BwSmem<MODE> lay; lay.Wp = 4 * p.GL; lay.nch = n;
         if (lay.total() * sizeof(float) + 1024 > 227 * 1024) continue;
         p.nch = n;

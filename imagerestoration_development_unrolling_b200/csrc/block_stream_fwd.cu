@@ -723,7 +723,9 @@ int glr_launch_gtv_coeffs(const glrgtv_shape& s, const float* w, float* c, void*
 #else
     const unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
 #endif
+    GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_WEIGHTS, stream);
     GLR_LAUNCH(k_gtv_coeffs, dim3(blocks ? blocks : 1), 256, 0, stream, (int)planes, s.H, s.W, w, c);
+    GLR_PROF_END(GLRGTV_SLOT_FWD_WEIGHTS, stream);
     return GLR_CHECK_LAUNCH();
 }
 

@@ -51,13 +51,17 @@ def launch_table(path, out):
     out.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for n, v in tot.most_common(30):
         out.write(f"| `{n}` | {cnt[n]} | {v / 1e3:.1f} | {100 * v / S:.1f}% |\n")
-    own = sum(v for n, v in tot.items() if "k_block" in n or "k_edge" in n)
-    out.write(f"\nown kernels (k_block_*, k_edge_*): {100 * own / S:.1f}% of the captured GPU time; the rest are the library "
-              "convolutions of the two feature projections and elementwise glue.\n\n")
+    own = sum(v for n, v in tot.items() if "void k_" in n or n.startswith("k_"))
+    out.write(f"\nown kernels (k_*): {100 * own / S:.1f}% of the captured GPU time; the rest are the library GEMMs of the two "
+              "feature projections (cuBLAS fp32 SIMT, TF32 off for parity) and elementwise glue.\n\n")
 
 
 def full_table(rep, out):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: an .ncu-rep, or the `ncu -i rep --page raw --csv` dump of one (reports can exceed gpurun's 64 MiB return limit)"""
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     out.write(f"## ncu --set full ({rep})\n\n")
@@ -73,10 +77,20 @@ def full_table(rep, out):
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     with open(f"profiles/{tag}_summary.md", "w") as out:
-        out.write(f"# ncu summary, round {tag}\n\nCommand: `python bench.py --steps N --warmup 3 --batch B --no-cpu-baseline` "
-                  "(launch list: B=8; full capture: B=4, first forward kernels at scale 0 and the last four backward kernels).\n"
-                  "Numbers under ncu are never bench values; they explain where the time goes.\n\n")
-        launch_table(f"gpurun_out/launches_{tag}.csv", out)
-        for part in ("fwd", "bwd"):
-            full_table(f"gpurun_out/prof_{tag}_{part}.ncu-rep", out)
+        out.write(f"# ncu summary, round {tag}\n\n"
+                  "Launch list and per-slot DRAM traffic: one step of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (the\n"
+                  "benchmark sizes, batch 32).  Full capture: `python tools/fwd_stage_times.py --scales 0 --reps 1 --bwd` - the 17\n"
+                  "streaming kernels of one forward + backward of the scale-0 block [32,48,256,256].\n"
+                  "Numbers under ncu are never bench values (cold cache, serialised); they explain where the time goes.\n\n")
+        launch_table(f"gpurun_out/launches_{tag}b.csv", out)
+        import json, os
+        sp = f"profiles/{tag}_step_slots.json"
+        if os.path.exists(sp):
+            d = json.load(open(sp))["slots"]
+            out.write("## per-slot totals of one step (tools/ncu_slots.py; DRAM bytes = dram__bytes_read.sum + dram__bytes_write.sum)\n\n"
+                      "| slot | launches | ncu ms | share of own kernels | DRAM GB |\n|---|---|---|---|---|\n")
+            for k, v in sorted(d.items(), key=lambda kv: -kv[1]["ncu_ms"]):
+                out.write(f"| {k} | {v['launches']} | {v['ncu_ms']:.3f} | {100 * v['share_of_own_kernels']:.1f}% | {v['dram_bytes'] / 1e9:.3f} |\n")
+            out.write("\n")
+        full_table(f"gpurun_out/prof_{tag}_stream_raw.csv", out)
     print("wrote", f"profiles/{tag}_summary.md")
