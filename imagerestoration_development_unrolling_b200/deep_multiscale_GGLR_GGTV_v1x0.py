@@ -36,6 +36,8 @@ def _edges_of(mask: np.ndarray):
     return [d for d, on in zip(itertools.product(offs, offs), mask.reshape(-1)) if on == 1]
 
 
+PROJ_TENSOR_CORES = False      # see MixtureGTVGLR._projections
+
 class _GraphOperatorBase(nn.Module):
     """State shared by GLRFast and GTVFast (V1X0:14-125, 243-356): the window, four per-channel
     stats_kernel_p* parameters and multiM."""
@@ -168,15 +170,22 @@ class MixtureGTVGLR(nn.Module):
     def _projections(self, patchs):
         """patchs_features_extraction00 / 01 (V1X0:556-612, 712, 725) as plain GEMMs on the Conv2d weights: a 1x1 conv is
         W[2C,C] @ x[C,HW]; the 2x2 stride-2 conv is the same after a space-to-depth.  cuBLAS serves these far better than
-        cuDNN's fp32 convolution fallbacks (profiles/r01_summary.md), and the parameters stay the reference's Conv2d's."""
+        cuDNN's fp32 convolution fallbacks; the parameters stay the reference's Conv2d's."""
         b, c, h, w = patchs.shape
         w00 = self.patchs_features_extraction00[0].weight.reshape(2 * c, c)
         w01a = self.patchs_features_extraction01[0].weight.reshape(c, 4 * c)
         w01b = self.patchs_features_extraction01[1].weight.reshape(2 * c, c)
-        bw = lambda m: m.unsqueeze(0).expand(b, -1, -1)      # batched GEMM keeps [B, out, HW] contiguous (no transposes)
-        feat0 = torch.bmm(bw(w00), patchs.reshape(b, c, h * w)).reshape(b, 2 * c, h, w)
+        # cuBLAS fp32 (SIMT) batched GEMM by default.  ops.proj_gemm (3xTF32 on the tensor cores through mma.sync, fp32-level
+        # accuracy, csrc/proj_gemm.cu) is available behind PROJ_TENSOR_CORES but MEASURED SLOWER on B200 (tools/proj_times.py:
+        # 0.93 vs 0.63 ms for the scale-0 forward GEMM): legacy mma.sync TF32 runs far below tcgen05 rates and 3x of it loses to
+        # the fp32 pipe.  A tcgen05 kind::tf32 kernel is what would pay here (DESIGN.md, next).
+        if PROJ_TENSOR_CORES and (h * w) % 16 == 0 and c % 4 == 0:
+            mm = lambda wm, x3: ops.proj_gemm(wm, x3, False)
+        else:
+            mm = lambda wm, x3: torch.bmm(wm.unsqueeze(0).expand(b, -1, -1), x3)
+        feat0 = mm(w00, patchs.reshape(b, c, h * w)).reshape(b, 2 * c, h, w)
         xs = nn.functional.pixel_unshuffle(patchs, 2).reshape(b, 4 * c, (h // 2) * (w // 2))
-        feat1 = torch.bmm(bw(w01b), torch.bmm(bw(w01a), xs)).reshape(b, 2 * c, h // 2, w // 2)
+        feat1 = mm(w01b, mm(w01a, xs)).reshape(b, 2 * c, h // 2, w // 2)
         return feat0, feat1
 
     def forward(self, patchs, _skip_weight=None):

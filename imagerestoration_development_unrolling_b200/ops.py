@@ -391,6 +391,45 @@ def _gn_setup(ctx, inputs, output):
 gather_neighbors.register_autograd(lambda ctx, g: (gather_neighbors_bwd(g, ctx.edges), None), setup_context=_gn_setup)
 
 
+# ====================================================================== feature projections (tensor-core 3xTF32 GEMMs)
+@torch.library.custom_op(f"{_NS}::proj_gemm", mutates_args=())
+def proj_gemm(w: Tensor, x: Tensor, transpose_w: bool) -> Tensor:
+    """w [M,K], x [B,K,N] -> [B,M,N] = w @ x   (transpose_w: x [B,M,N] -> [B,K,N] = w^T @ x); glrgtv_proj_gemm"""
+    _chk(w, x)
+    w, x = _c(w), _c(x)
+    M, K = w.shape
+    B, R, N = x.shape
+    if R != (M if transpose_w else K):
+        raise RuntimeError(f"proj_gemm: weight {tuple(w.shape)} does not match input {tuple(x.shape)}")
+    y = x.new_empty(B, K if transpose_w else M, N)
+    _call("glrgtv_proj_gemm", x, int(bool(transpose_w)), B, M, N, K, w, x, y)
+    return y
+
+
+@proj_gemm.register_fake
+def _(w, x, transpose_w):
+    M, K = w.shape
+    return x.new_empty(x.shape[0], K if transpose_w else M, x.shape[2])
+
+
+def _pg_setup(ctx, inputs, output):
+    w, x, transpose_w = inputs
+    ctx.save_for_backward(w, x)
+    ctx.transpose_w = transpose_w
+
+
+def _pg_backward(ctx, gy):
+    w, x = ctx.saved_tensors
+    gy = _c(gy)
+    gx = proj_gemm(w, gy, not ctx.transpose_w)
+    # weight gradient: one reduction over batch and pixels - cuBLAS (split-K), [M,K] = sum_b gy[b] x[b]^T (or its transpose)
+    gw = (torch.bmm(x, gy.transpose(1, 2)) if ctx.transpose_w else torch.bmm(gy, x.transpose(1, 2))).sum(0)
+    return gw, gx, None
+
+
+proj_gemm.register_autograd(_pg_backward, setup_context=_pg_setup)
+
+
 # ====================================================================== the fused block (hot path)
 # params layout: for each of GTVmodule00, GLRmodule00, GTVmodule01, GLRmodule01: p01, p02a, p02b, p03, multiM (20),
 # then alphaCGD, betaCGD, muys00, ro00, gamma00, muys01, ro01, gamma01 (8), then optionally skip_weight (1).

@@ -227,6 +227,15 @@ int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params* p, const 
                      const float* gout, float* gx, float* gfeat0, float* gfeat1,
                      const glrgtv_block_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Feature projections patchs_features_extraction00 / 01 (V1X0:556-612, 712, 725): tensor-core GEMMs with 3xTF32
+ * error compensation (fp32-level accuracy).  All operands row-major, contiguous, 16-byte aligned; M, N, K % 4 == 0.
+ *   transpose_w == 0:  Y[b] (M x N) = W (M x K)   . X[b] (K x N)      forward of a 1x1 (or space-to-depth 2x2) conv
+ *   transpose_w == 1:  Y[b] (K x N) = W^T (K x M) . X[b] (M x N)      its input gradient
+ * ---------------------------------------------------------------------------------------------- */
+int glrgtv_proj_gemm(int transpose_w, int batch, int M, int N, int K, const float* W, const float* X, float* Y,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,3 +125,20 @@ def test_soft_pool_normalize_gather(ops, shape):
 def test_cpu_tensors_are_refused(ops):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.pool2(torch.zeros(1, 1, 1, 2, 2))
+
+
+@pytest.mark.parametrize("shape", [(2, 96, 48, 64 * 64), (1, 48, 192, 32 * 32), (3, 384, 1536, 16 * 16), (2, 768, 384, 256)])
+def test_projection_gemm_3xtf32(shape):
+    """glrgtv_proj_gemm (tensor cores, 3xTF32) against an fp64 GEMM: fp32-level accuracy, forward and both gradients"""
+    from imagerestoration_development_unrolling_b200 import ops
+    B, M, K, N = shape
+    gen = torch.Generator().manual_seed(M + K)
+    w = torch.randn(M, K, generator=gen).cuda().requires_grad_(True)
+    x = torch.randn(B, K, N, generator=gen).cuda().requires_grad_(True)
+    gy = torch.randn(B, M, N, generator=gen).cuda()
+    y = ops.proj_gemm(w, x, False)
+    gw, gx = torch.autograd.grad(y, [w, x], gy)
+    w64, x64, gy64 = w.detach().double(), x.detach().double(), gy.double()
+    assert rel(y, torch.einsum("mk,bkn->bmn", w64, x64)) < 2e-6
+    assert rel(gx, torch.einsum("mk,bmn->bkn", w64, gy64)) < 2e-6
+    assert rel(gw, torch.einsum("bmn,bkn->mk", gy64, x64)) < 1e-5
