@@ -210,6 +210,9 @@ int glrgtv_set_block_path(int mode);
 /* Loader of the streaming kernels: 0 = automatic (per stage, as measured), 1 = per-thread cp.async rings,
  * 2 = one producer warp issuing TMA bulk row copies (cp.async.bulk + mbarrier).  Same results; a tuning switch. */
 int glrgtv_set_stream_loader(int mode);
+/* Edge-weight gradient kernel of the streaming backward: 0 = tiled (block_gw.cu, default), 1 = streaming walkers
+ * (block_gw_stream.cu) where their range allows.  Same results; a tuning switch. */
+int glrgtv_set_gw_kernel(int streaming);
 /* streaming-path kernels launched since the library was loaded (diagnostic: lets a test assert which path ran) */
 unsigned long long glrgtv_stream_launch_count(void);
 

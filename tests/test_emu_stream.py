@@ -45,9 +45,11 @@ def test_stream_block_forward(case):
     assert rel(out, ref_out) < 1e-5
 
 
+@pytest.mark.parametrize("gw_streaming", [0, 1], ids=["gw_tiled", "gw_stream"])
 @pytest.mark.parametrize("case", CASES)
-def test_stream_block_backward(case):
+def test_stream_block_backward(case, gw_streaming):
     dim, G, B, H, W = case
+    E.emu_lib().glrgtv_set_gw_kernel(gw_streaming)
     F = dim // G
     sd = random_block_state(dim, G, seed=400 + H)
     gen = torch.Generator().manual_seed(H * W + 1)
@@ -77,5 +79,6 @@ def test_stream_block_backward(case):
     got.update({k: g for k, g in zip(names, gfeat[1:])})
     errs = {k: (rel(got[k], ref) if float(ref.abs().max()) > 0 else float(got[k].abs().max())) for k, ref in pg_ref.items()}
     errs["gx"] = rel(gx_total, gx_ref)
+    E.emu_lib().glrgtv_set_gw_kernel(0)
     bad = {k: v for k, v in errs.items() if v > 2e-4}
     assert not bad, bad
