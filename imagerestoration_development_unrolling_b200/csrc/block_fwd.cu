@@ -398,7 +398,7 @@ int glr_block_params_ok(const glrgtv_shape* s, const glrgtv_block_params* p) {
 
 // block_stream_fwd.cu
 extern int g_glr_block_path;
-int glr_stream_eligible(const glrgtv_shape* s);
+int glr_stream_fwd_eligible(const glrgtv_shape* s);
 int glr_launch_gtv_coeffs(const glrgtv_shape& s, const float* w, float* c, void* stream);
 int glr_stream_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, const float* x, float* out,
                          const glrgtv_block_saved* sv, void* stream);
@@ -424,7 +424,7 @@ extern "C" int glrgtv_block_fwd(const glrgtv_shape* s, const glrgtv_block_params
     if ((rc = launch_weights(sc, feat1, p->gtv1.multiM, p->glr1.multiM, sv->wT1, sv->wL1, stream))) return rc;
 
     // register-streaming stage kernels (block_stream_fwd.cu) where the shape allows, else the plane kernels below
-    const bool can_stream = glr_stream_eligible(s) && sv->cT0 && sv->cT1 && glr_aligned16(sv->cT0) && glr_aligned16(sv->cT1);
+    const bool can_stream = glr_stream_fwd_eligible(s) && sv->cT0 && sv->cT1 && glr_aligned16(sv->cT0) && glr_aligned16(sv->cT1);
     if (g_glr_block_path == 2 && !can_stream) return GLRGTV_ERR_UNSUPPORTED;
     if (can_stream && g_glr_block_path != 1) {
         if ((rc = glr_launch_gtv_coeffs(*s, sv->wT0, sv->cT0, stream))) return rc;

@@ -31,6 +31,7 @@ struct StreamFwdArgs {
     int nch;        // channels per CTA (divides F)
     int band_rows;  // fine rows per CTA (even)
     int n_bands;
+    int n_strips;   // column strips (planes wider than a 64-lane walker): STREAM_STRIP valid columns each, 8 columns of halo per side
 };
 
 // one resolution of one walker
@@ -62,6 +63,7 @@ struct Lvl {
 #define STREAM_OPR 4
 #define STREAM_WR 4
 #define STREAM_NBAR 4
+#define STREAM_STRIP 240   // valid output columns of one strip of a wide plane (256-column walker minus 2 x 8 halo columns)
 #ifndef STREAM_PHASES
 #define STREAM_PHASES 0   // 0: per stage (see stream_walk), 1: rotated windows everywhere, 3: phase-unrolled everywhere
 #endif
@@ -88,12 +90,14 @@ struct StreamSmem {
 // geometry of one CTA, shared by the walkers and the producer
 struct StreamCta {
     int H, W, F, G, nch, b, g, f0, R0, R1, K0, M, Wp;
+    int x0, v0, v1;      // first column of the walker's window; valid output columns [v0, v1)
     size_t HW;
 };
 __device__ __forceinline__ StreamCta stream_cta(const StreamFwdArgs& a, int GL) {
     StreamCta c;
     c.H = a.s.H; c.W = a.s.W; c.F = a.s.F; c.G = a.s.G; c.nch = a.nch;
     int bid = (int)blockIdx.x;
+    const int strip = bid % a.n_strips; bid /= a.n_strips;
     const int band = bid % a.n_bands; bid /= a.n_bands;
     const int chunks = c.F / c.nch;
     const int chunk = bid % chunks; bid /= chunks;
@@ -103,6 +107,13 @@ __device__ __forceinline__ StreamCta stream_cta(const StreamFwdArgs& a, int GL) 
     c.R1 = c.R0 + a.band_rows < c.H ? c.R0 + a.band_rows : c.H;
     c.K0 = c.R0 / 2;
     c.M = (c.R1 - c.R0) + 6 + STREAM_DF;
+    if (a.n_strips > 1) {
+        c.v0 = strip * STREAM_STRIP;
+        c.v1 = c.v0 + STREAM_STRIP < c.W ? c.v0 + STREAM_STRIP : c.W;
+        c.x0 = strip ? c.v0 - 8 : 0;
+    } else {
+        c.x0 = 0; c.v0 = 0; c.v1 = c.W;
+    }
     c.Wp = 4 * GL;
     c.HW = (size_t)c.H * c.W;
     return c;
@@ -248,7 +259,8 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
     }
 
     LaneCtx lc;
-    lc.col0 = 4 * lane;
+    const int lcol = 4 * lane;                             // column inside the walker's window (shared-memory rings)
+    lc.col0 = (FINE ? ct.x0 : ct.x0 / 2) + lcol;           // column in the image plane of this resolution
     lc.width = FINE ? (GL < 32 ? GL : 32) : (GL / 2 < 32 ? GL / 2 : 32);
     lc.active = live && lc.col0 < L.W;
     lc.first = lc.col0 == 0;
@@ -268,7 +280,7 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
     const bool has_skip = MODE == MODE_X3 && a.p.skip != nullptr;
 
     const int r0 = FINE ? R0 : ct.K0;
-    auto wrow = [&](int pl, int row) { return wring + (pl * STREAM_WR + (row & (STREAM_WR - 1))) * wpitch + lc.col0; };
+    auto wrow = [&](int pl, int row) { return wring + (pl * STREAM_WR + (row & (STREAM_WR - 1))) * wpitch + lcol; };
 
     // ---- cp.async loader (TMA == false): every thread stages its own share STREAM_PD block steps ahead.
     //      weight planes wk, wk+nwk, ... of this role's level (src at row 0, ring address, row lead), this lane's quad
@@ -293,7 +305,7 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
                 const float* base = FINE ? (set == 0 ? a.cT0 + plane * 2 * LHW : (set == 1 ? a.wL0 : a.wT0) + plane * 4 * LHW)
                                          : (set == 0 ? a.cT1 + plane * 2 * LHW : (set == 1 ? a.wL1 : a.wT1) + plane * 4 * LHW);
                 wsrc[j] = base + (size_t)e * LHW + lc.col0;
-                wdst[j] = smem_advance(sbase, (int)(FINE ? lay.w0ring() : lay.w1ring()) + pl * STREAM_WR * wpitch + lc.col0);
+                wdst[j] = smem_advance(sbase, (int)(FINE ? lay.w0ring() : lay.w1ring()) + pl * STREAM_WR * wpitch + lcol);
                 wlead[j] = set == 2 && e == 0;             // wT plane U runs one row ahead
             }
         }
@@ -302,8 +314,8 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
             if (MODE == MODE_X3) { opp[1] = a.bB_in + off + lc.col0; opp[2] = a.r1_in + off + lc.col0; }
         }
     }
-    const smem_addr_t opdst = smem_advance(sbase, (int)lay.opring() + (live ? wk : 0) * NOP * STREAM_OPR * Wp + lc.col0);
-    const smem_addr_t zdst = smem_advance(sbase, (int)lay.zring() + (live ? wk : 0) * ZR * Wp + 2 * lc.col0);
+    const smem_addr_t opdst = smem_advance(sbase, (int)lay.opring() + (live ? wk : 0) * NOP * STREAM_OPR * Wp + lcol);
+    const smem_addr_t zdst = smem_advance(sbase, (int)lay.zring() + (live ? wk : 0) * ZR * Wp + 2 * lcol);
     auto issue = [&](int mt) {
         if (mt >= M) return;
         if (FINE ? (mt < STREAM_DF) : (mt & 1)) return;
@@ -348,7 +360,7 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
                 if (lead ? !ok1 : !ok0) continue;
                 const float* base = FINE ? (set == 0 ? a.cT0 + plane * 2 * LHW : (set == 1 ? a.wL0 : a.wT0) + plane * 4 * LHW)
                                          : (set == 0 ? a.cT1 + plane * 2 * LHW : (set == 1 ? a.wL1 : a.wT1) + plane * 4 * LHW);
-                cp_async16_s(smem_advance(sbase, (int)(FINE ? lay.w0ring() : lay.w1ring()) + pl * STREAM_WR * wpitch + lc.col0 + (lead ? so1 : so0)),
+                cp_async16_s(smem_advance(sbase, (int)(FINE ? lay.w0ring() : lay.w1ring()) + pl * STREAM_WR * wpitch + lcol + (lead ? so1 : so0)),
                              base + (size_t)e * LHW + lc.col0 + (lead ? go1 : go0));
             }
         }
@@ -409,9 +421,9 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
             //      (written into the centre slot the moment row 0 arrives), rows below the image repeat row H-1.
             if (t >= 0 && t < L.H) {
                 if (FINE) {
-                    z[N] = row_ld(zring + zs * Wp + lc.col0);
+                    z[N] = row_ld(zring + zs * Wp + lcol);
                 } else {
-                    const float* p0 = zring + zs * Wp + 2 * lc.col0;
+                    const float* p0 = zring + zs * Wp + 2 * lcol;
                     const Row a0 = row_ld(p0), a1 = row_ld(p0 + 4), b0 = row_ld(p0 + Wp), b1 = row_ld(p0 + Wp + 4);
                     z[N].v[0] = 0.25f * (a0.v[0] + a0.v[1] + b0.v[0] + b0.v[1]);
                     z[N].v[1] = 0.25f * (a0.v[2] + a0.v[3] + b0.v[2] + b0.v[3]);
@@ -519,7 +531,7 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
                     if (!FINE) {
                         // coarse: hand 0.25 * (coarse term) to the fine epilogue of rows 2r, 2r+1
                         if (lc.active) {
-                            float* slot = cring + (r & 1) * NRING * Wpc + lc.col0;
+                            float* slot = cring + (r & 1) * NRING * Wpc + lcol;
                             float v[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) v[j] = 0.25f * Az.v[j];
@@ -531,9 +543,9 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
                             }
                         }
                     } else {
-                        const float* slot = cring + ((r >> 1) & 1) * NRING * Wpc + (lc.col0 >> 1);
+                        const float* slot = cring + ((r >> 1) & 1) * NRING * Wpc + (lcol >> 1);
                         const float2 cz = *reinterpret_cast<const float2*>(slot);
-                        const Row zq = row_ld(zring + zqs * Wp + lc.col0);      // row t-3 is still in the ring
+                        const Row zq = row_ld(zring + zqs * Wp + lcol);      // row t-3 is still in the ring
 #pragma unroll
                         for (int j = 0; j < 4; ++j) Az.v[j] += zq.v[j] + (j < 2 ? cz.x : cz.y);
                         if (THR) {
@@ -541,7 +553,7 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
 #pragma unroll
                             for (int j = 0; j < 4; ++j) rT.v[j] += (j < 2 ? ctv.x : ctv.y);
                         }
-                        const float* ops = opring + (r & (STREAM_OPR - 1)) * Wp + lc.col0;
+                        const float* ops = opring + (r & (STREAM_OPR - 1)) * Wp + lcol;
                         Row in0 = row_zero(), in1 = row_zero(), in2 = row_zero(), o0, o1, o2;
                         if (MODE == MODE_X2 || has_skip) in0 = row_ld(ops);
                         if (MODE == MODE_X3) { in1 = row_ld(ops + STREAM_OPR * Wp); in2 = row_ld(ops + 2 * STREAM_OPR * Wp); }
@@ -562,7 +574,7 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
                                 o0.v[j] = has_skip ? s0 * in0.v[j] + s1 * x3 : x3;
                             }
                         }
-                        if (lc.active) {
+                        if (lc.active && lc.col0 >= ct.v0 && lc.col0 < ct.v1) {
                             const size_t gi = off + (size_t)r * W + lc.col0;
                             st4(a.out0 + gi, o0.v);
                             if (MODE == MODE_X2) { st4(a.out1 + gi, o1.v); st4(a.out2 + gi, o2.v); }
@@ -645,16 +657,22 @@ extern "C" int glrgtv_set_block_path(int mode) {
     return GLRGTV_OK;
 }
 
+// backward (and the TMA loader): a walker spans the whole row, at most two warps
 int glr_stream_eligible(const glrgtv_shape* s) {
     return s->W % 8 == 0 && s->W <= 256 && s->H % 2 == 0 && s->H >= 2;
 }
+// forward: wider planes are cut into column strips of STREAM_STRIP valid columns (4K inference)
+int glr_stream_fwd_eligible(const glrgtv_shape* s) {
+    return s->W % 8 == 0 && s->H % 2 == 0 && s->H >= 2;
+}
 
 struct StreamPlan {
-    int GL, nch, threads, band_rows, n_bands;
+    int GL, nch, threads, band_rows, n_bands, n_strips;
 };
 static StreamPlan stream_plan(const glrgtv_shape& s) {
     StreamPlan p;
     p.GL = s.W > 128 ? 64 : s.W > 64 ? 32 : s.W > 32 ? 16 : 8;
+    p.n_strips = s.W > 256 ? (s.W + STREAM_STRIP - 1) / STREAM_STRIP : 1;
     p.nch = 1;
     for (int n = 1; n <= s.F; ++n) {
         if (s.F % n) continue;
@@ -663,9 +681,9 @@ static StreamPlan stream_plan(const glrgtv_shape& s) {
     }
     p.threads = ((p.nch * p.GL + 31) & ~31) + ((p.nch * p.GL / 2 + 31) & ~31);
     // whole-height bands unless the grid would leave SMs idle
-    const long ctas = (long)s.B * s.G * (s.F / p.nch);
+    const long ctas = (long)s.B * s.G * (s.F / p.nch) * p.n_strips;
     int bands = 1;
-    while (ctas * bands < 296 && s.H / (bands * 2) >= 32) bands *= 2;
+    while (ctas * bands < 592 && s.H / (bands * 2) >= 64) bands *= 2;
     p.band_rows = ((s.H + bands - 1) / bands + 1) & ~1;
     p.n_bands = (s.H + p.band_rows - 1) / p.band_rows;
     return p;
@@ -701,14 +719,14 @@ template <int MODE>
 static int launch_stream_stage(StreamFwdArgs a, void* stream) {
     const glrgtv_shape& s = a.s;
     const StreamPlan p = stream_plan(s);
-    a.nch = p.nch; a.band_rows = p.band_rows; a.n_bands = p.n_bands;
-    const long blocks = (long)s.B * s.G * (s.F / p.nch) * p.n_bands;
+    a.nch = p.nch; a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.n_strips = p.n_strips;
+    const long blocks = (long)s.B * s.G * (s.F / p.nch) * p.n_bands * p.n_strips;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
     GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_BA + MODE, stream);
     // the TMA producer keeps at most 32 * STREAM_MAXI row copies per batch
     const int nf = StreamSmem<MODE>::NPL + p.nch * StreamSmem<MODE>::NOP, nc = StreamSmem<MODE>::NPL + 2 * p.nch;
     const bool want_tma = g_glr_stream_loader == 2 || (g_glr_stream_loader == 0 && MODE == MODE_X2 && s.W >= 128);
-    const bool tma = want_tma && 2 * nf + nc <= 32 * STREAM_MAXI;
+    const bool tma = want_tma && 2 * nf + nc <= 32 * STREAM_MAXI && p.n_strips == 1;      // (the TMA producer copies whole rows)
     const int rc = p.GL == 64 ? (tma ? launch_stream_kernel<MODE, true, true>(a, p, blocks, stream) : launch_stream_kernel<MODE, true, false>(a, p, blocks, stream))
                               : (tma ? launch_stream_kernel<MODE, false, true>(a, p, blocks, stream) : launch_stream_kernel<MODE, false, false>(a, p, blocks, stream));
     GLR_PROF_END(GLRGTV_SLOT_FWD_BA + MODE, stream);
@@ -737,7 +755,7 @@ int glr_stream_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, co
     a.s = *s; a.p = *p;
     a.wT0 = sv->wT0; a.wL0 = sv->wL0; a.wT1 = sv->wT1; a.wL1 = sv->wL1; a.cT0 = sv->cT0; a.cT1 = sv->cT1;
     a.y = nullptr; a.bB_in = nullptr; a.r1_in = nullptr; a.out1 = nullptr; a.out2 = nullptr;
-    a.nch = 1; a.band_rows = s->H; a.n_bands = 1;
+    a.nch = 1; a.band_rows = s->H; a.n_bands = 1; a.n_strips = 1;
     a.z = x; a.out0 = sv->bA;
     if ((rc = launch_stream_stage<MODE_BA>(a, stream))) return rc;
     a.z = sv->bA; a.out0 = sv->x1;

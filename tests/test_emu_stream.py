@@ -23,7 +23,11 @@ def stream_path(request):
     E.emu_lib().glrgtv_set_stream_loader(0)
 
 
-@pytest.mark.parametrize("case", CASES)
+# planes wider than one 64-lane walker are cut into column strips (forward only): 2 and 3 strips, ragged last strip
+WIDE = [(6, 1, 1, 8, 272), (4, 2, 1, 6, 504), (2, 1, 1, 4, 488)]
+
+
+@pytest.mark.parametrize("case", CASES + WIDE)
 def test_stream_block_forward(case):
     dim, G, B, H, W = case
     F = dim // G

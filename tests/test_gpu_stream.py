@@ -90,15 +90,32 @@ def test_streaming_equals_plane_kernels_at_benchmark_resolution(M, lib, case):
             assert rel(pg2[k], pg1[k]) < tol, (k, rel(pg2[k], pg1[k]))
 
 
-def test_wide_planes_take_the_plane_kernels(M, lib):
-    """W > 256 is outside the streaming kernels' range: automatic mode falls back to the plane kernels, forced mode raises"""
-    dim, G = 12, 2
-    blk = make_block(M, dim, G, random_block_state(dim, G, seed=1))
-    x = torch.randn(1, dim, 8, 264).cuda()
+def test_wide_planes(M, lib):
+    """W > 256: the forward streams in column strips (4K inference), the backward takes the plane kernels; both exact"""
+    dim, G, B, H, W = 12, 2, 1, 24, 520
+    sd = random_block_state(dim, G, seed=1)
+    gen = torch.Generator().manual_seed(9)
+    x, gout = torch.randn(B, dim, H, W, generator=gen), torch.randn(B, dim, H, W, generator=gen)
+    ref = O.lowpass_block_fwd_bwd({k: v.double() for k, v in sd.items()}, x.double(), gout.double())
     n0 = lib.glrgtv_stream_launch_count()
-    with torch.no_grad():
-        blk(x)
-    assert lib.glrgtv_stream_launch_count() == n0
+    out, gx, pg = run_block(make_block(M, dim, G, sd), x, gout)
+    assert lib.glrgtv_stream_launch_count() - n0 == 4          # the four forward stages; no streaming backward kernels
+    check_against(out, gx, pg, *ref)
     lib.glrgtv_set_block_path(2)
-    with pytest.raises(RuntimeError, match="UNSUPPORTED"), torch.no_grad():
-        blk(x)
+    with pytest.raises(RuntimeError, match="UNSUPPORTED"):
+        run_block(make_block(M, dim, G, sd), x, gout)
+
+
+def test_4k_row_forward(M, lib):
+    """a 3840-wide band (16 strips) against the plane kernels"""
+    dim, G = 48, 8
+    blk = make_block(M, dim, G, random_block_state(dim, G, seed=2))
+    x = torch.randn(1, dim, 64, 3840, generator=torch.Generator().manual_seed(4)).cuda()
+    with torch.no_grad():
+        lib.glrgtv_set_block_path(1)
+        ref = blk(x)
+        lib.glrgtv_set_block_path(0)
+        n0 = lib.glrgtv_stream_launch_count()
+        out = blk(x)
+        assert lib.glrgtv_stream_launch_count() - n0 == 4
+    assert rel(out, ref) < 2e-6
