@@ -18,6 +18,9 @@ enum { GW_X3 = BW_X3, GW_X2 = BW_X2A, GW_X1 = BW_X1, GW_BA = BW_BA };   // GW_X2
 #define GW_TH 16
 #define GW_TW 32
 #define GW_NT 256
+#ifndef GW_MINB
+#define GW_MINB 4
+#endif
 #define GW_PPT ((GW_TH * GW_TW) / GW_NT)
 #define GW_ZH (GW_TH + 4)
 #define GW_ZW (GW_TW + 4)
@@ -29,7 +32,7 @@ enum { GW_X3 = BW_X3, GW_X2 = BW_X2A, GW_X1 = BW_X1, GW_BA = BW_BA };   // GW_X2
 // MODE GW_X2 does the linear part (upstream gA) and the thresholded part (upstream gB) of stage X2 in one pass: both read
 // z = x1 and the same two source tensors.
 template <int MODE, bool COARSE>
-__global__ void __launch_bounds__(GW_NT) k_gw_stage(GwArgs a) {
+__global__ void __launch_bounds__(GW_NT, GW_MINB) k_gw_stage(GwArgs a) {
     GLR_SMEM_DECL(smem);
     constexpr bool HAS_L = MODE != GW_BA, X2 = MODE == GW_X2;
     constexpr int TH = GW_TH, TW = GW_TW, ZH = GW_ZH, ZW = GW_ZW, SH = GW_SH, SW = GW_SW;
