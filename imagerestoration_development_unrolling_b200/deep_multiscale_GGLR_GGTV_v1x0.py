@@ -182,7 +182,7 @@ class MixtureGTVGLR(nn.Module):
         if PROJ_TENSOR_CORES and (h * w) % 16 == 0 and c % 4 == 0:
             mm = lambda wm, x3: ops.proj_gemm(wm, x3, False)
         else:
-            mm = lambda wm, x3: torch.bmm(wm.unsqueeze(0).expand(b, -1, -1), x3)
+            mm = ops.projection                       # cuBLAS fp32 forward / input gradient, split-reduction weight gradient
         feat0 = mm(w00, patchs.reshape(b, c, h * w)).reshape(b, 2 * c, h, w)
         xs = nn.functional.pixel_unshuffle(patchs, 2).reshape(b, 4 * c, (h // 2) * (w // 2))
         feat1 = mm(w01b, mm(w01a, xs)).reshape(b, 2 * c, h // 2, w // 2)

@@ -430,6 +430,57 @@ def _pg_backward(ctx, gy):
 proj_gemm.register_autograd(_pg_backward, setup_context=_pg_setup)
 
 
+# ---- projection with a library forward / input gradient and the split-reduction weight-gradient kernel
+def proj_wgrad_supported(M: int, K: int, N: int) -> bool:
+    return N % 32 == 0 and ((M % 96 == 0 and K % 48 == 0) or (K % 96 == 0 and M % 48 == 0))
+
+
+@torch.library.custom_op(f"{_NS}::proj_wgrad", mutates_args=())
+def proj_wgrad(gy: Tensor, x: Tensor) -> Tensor:
+    """gy [B,M,N], x [B,K,N] -> gw [M,K] = sum_b gy[b] @ x[b]^T   (glrgtv_proj_wgrad)"""
+    _chk(gy, x)
+    gy, x = _c(gy), _c(x)
+    B, M, N = gy.shape
+    K = x.shape[1]
+    gw = gy.new_zeros(M, K)
+    _call("glrgtv_proj_wgrad", gy, B, M, N, K, gy, x, gw)
+    return gw
+
+
+@proj_wgrad.register_fake
+def _(gy, x):
+    return gy.new_empty(gy.shape[1], x.shape[1])
+
+
+class _Projection(torch.autograd.Function):
+    """y[b] = w @ x[b]: cuBLAS fp32 for y and gx, csrc/proj_wgrad.cu for gw (cuBLAS' batched GEMM + sum leaves most of the
+    GPU idle on this tiny-output, long-reduction shape)."""
+
+    @staticmethod
+    def forward(ctx, w, x):
+        ctx.save_for_backward(w, x)
+        return torch.bmm(w.unsqueeze(0).expand(x.shape[0], -1, -1), x)
+
+    @staticmethod
+    def backward(ctx, gy):
+        w, x = ctx.saved_tensors
+        gy = _c(gy)
+        gx = torch.bmm(w.t().unsqueeze(0).expand(x.shape[0], -1, -1), gy) if ctx.needs_input_grad[1] else None
+        gw = None
+        if ctx.needs_input_grad[0]:
+            # measured on B200 (tools/proj_times.py): the split-reduction kernel runs at ~31 TFLOP/s whatever the shape; cuBLAS
+            # beats that once the output tile grid is large enough to fill the GPU (M*K above ~10K), and loses 2.7x below
+            if proj_wgrad_supported(w.shape[0], w.shape[1], x.shape[2]) and w.shape[0] * w.shape[1] <= 9216:
+                gw = proj_wgrad(gy, x)
+            else:
+                gw = torch.bmm(gy, x.transpose(1, 2)).sum(0)
+        return gw, gx
+
+
+def projection(w: Tensor, x: Tensor) -> Tensor:
+    return _Projection.apply(w, x)
+
+
 # ====================================================================== the fused block (hot path)
 # params layout: for each of GTVmodule00, GLRmodule00, GTVmodule01, GLRmodule01: p01, p02a, p02b, p03, multiM (20),
 # then alphaCGD, betaCGD, muys00, ro00, gamma00, muys01, ro01, gamma01 (8), then optionally skip_weight (1).

@@ -238,6 +238,10 @@ int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params* p, const 
  * ---------------------------------------------------------------------------------------------- */
 int glrgtv_proj_gemm(int transpose_w, int batch, int M, int N, int K, const float* W, const float* X, float* Y,
                      void* stream);
+/* Weight gradient of the same projections: gW [M,K] += sum_b gY[b] (M x N) . X[b]^T (N x K), fp32 FMA, the reduction
+ * over batch and pixels split across the grid (ACCUMULATES: the caller zeroes gW).  N % 32 == 0 and (M % 96 == 0,
+ * K % 48 == 0) or (K % 96 == 0, M % 48 == 0); GLRGTV_ERR_UNSUPPORTED otherwise. */
+int glrgtv_proj_wgrad(int batch, int M, int N, int K, const float* gY, const float* X, float* gW, void* stream);
 
 #ifdef __cplusplus
 }

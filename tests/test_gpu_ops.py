@@ -142,3 +142,21 @@ def test_projection_gemm_3xtf32(shape):
     assert rel(y, torch.einsum("mk,bkn->bmn", w64, x64)) < 2e-6
     assert rel(gx, torch.einsum("mk,bmn->bkn", w64, gy64)) < 2e-6
     assert rel(gw, torch.einsum("bmn,bkn->mk", gy64, x64)) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(4, 96, 48, 64 * 64), (2, 48, 192, 32 * 32), (2, 192, 96, 1024), (1, 768, 384, 256), (3, 96, 384, 64)])
+def test_projection_weight_gradient_kernel(shape):
+    """glrgtv_proj_wgrad (split-reduction fp32 GEMM) against an fp64 reference, through ops.projection's autograd"""
+    from imagerestoration_development_unrolling_b200 import ops
+    B, M, K, N = shape
+    assert ops.proj_wgrad_supported(M, K, N)
+    gen = torch.Generator().manual_seed(M * K)
+    w = torch.randn(M, K, generator=gen).cuda().requires_grad_(True)
+    x = torch.randn(B, K, N, generator=gen).cuda().requires_grad_(True)
+    gy = torch.randn(B, M, N, generator=gen).cuda()
+    y = ops.projection(w, x)
+    gw, gx = torch.autograd.grad(y, [w, x], gy)
+    w64, x64, gy64 = w.detach().double(), x.detach().double(), gy.double()
+    assert rel(y, torch.einsum("mk,bkn->bmn", w64, x64)) < 2e-6
+    assert rel(gx, torch.einsum("mk,bmn->bkn", w64, gy64)) < 2e-6
+    assert rel(gw, torch.einsum("bmn,bkn->mk", gy64, x64)) < 5e-6

@@ -14,6 +14,7 @@ for (B,M,K,N) in [(32,96,48,65536),(32,48,192,16384),(32,192,96,16384),(32,768,3
     r={}
     r['fwd_tc']=t(lambda: ops.proj_gemm(w,x,False)); r['fwd_bmm']=t(lambda: torch.bmm(we,x))
     r['dgrad_tc']=t(lambda: ops.proj_gemm(w,gy,True)); r['dgrad_bmm']=t(lambda: torch.bmm(we.transpose(1,2),gy))
-    r['wgrad_einsum']=t(lambda: torch.einsum("bmn,bkn->mk",gy,x)); r['wgrad_bmmsum']=t(lambda: torch.bmm(gy,x.transpose(1,2)).sum(0))
+    r['wgrad_bmmsum']=t(lambda: torch.bmm(gy,x.transpose(1,2)).sum(0))
+    if ops.proj_wgrad_supported(M,K,N): r['wgrad_own']=t(lambda: ops.proj_wgrad(gy,x))
     gf=2*B*M*K*N/1e9
     print((B,M,K,N), f"{gf:.1f} GFLOP", {k: round(v,3) for k,v in r.items()})
