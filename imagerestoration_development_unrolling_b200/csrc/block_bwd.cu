@@ -717,13 +717,8 @@ static int launch_bwd_stage_gen(const BlockBwdArgs& a, void* stream) {
     constexpr size_t smem = (size_t)BwdLayout<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS, GEN>::total * sizeof(float);
     static_assert(smem <= 227 * 1024, "backward tile does not fit shared memory");
 #ifndef GLRGTV_EMU
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS, GEN>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return glr_record_launch_error();
-        configured = true;
-    }
+    static size_t optin[GLR_MAX_DEVICES] = {0};
+    if (int rc_ = glr_smem_optin(k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS, GEN>, smem, optin)) return rc_;
 #endif
     GLR_PROF_BEGIN(GLRGTV_SLOT_BWD_X3 + MODE, stream);
     GLR_LAUNCH((k_block_bwd_stage<MODE, GLR_BTH, GLR_BTW, GLR_BWD_THREADS, GEN>), dim3((unsigned)blocks), GLR_BWD_THREADS,

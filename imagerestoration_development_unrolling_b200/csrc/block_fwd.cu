@@ -339,13 +339,8 @@ static int launch_stage_gen(const BlockFwdArgs& a, void* stream) {
     constexpr size_t smem = (size_t)FwdLayout<MODE, GLR_TH, GLR_TW, NT, GEN>::total * sizeof(float);
     static_assert(smem <= 227 * 1024, "forward tile does not fit shared memory");
 #ifndef GLRGTV_EMU
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_block_stage<MODE, GLR_TH, GLR_TW, NT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess)
-            return glr_record_launch_error();
-        configured = true;
-    }
+    static size_t optin[GLR_MAX_DEVICES] = {0};
+    if (int rc_ = glr_smem_optin(k_block_stage<MODE, GLR_TH, GLR_TW, NT, GEN>, smem, optin)) return rc_;
 #endif
     GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_BA + MODE, stream);
     GLR_LAUNCH((k_block_stage<MODE, GLR_TH, GLR_TW, NT, GEN>), dim3((unsigned)blocks), NT, smem, stream, a);

@@ -330,12 +330,8 @@ static int launch_gs(const GwArgs& a, int threads, void* stream) {
     lay.Wl = 4 * GL; lay.Wr = COARSE ? 8 * GL : 4 * GL; lay.F = a.s.F;
     const size_t smem = lay.total() * sizeof(float);
 #ifndef GLRGTV_EMU
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(k_gw_stream<MODE, XW, COARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return glr_record_launch_error();
-        configured = smem;
-    }
+    static size_t optin[GLR_MAX_DEVICES] = {0};
+    if (int rc_ = glr_smem_optin(k_gw_stream<MODE, XW, COARSE>, smem, optin)) return rc_;
 #endif
     ++g_glr_stream_launches;
     GLR_LAUNCH_FIBERS((k_gw_stream<MODE, XW, COARSE>), dim3((unsigned)(a.s.B * a.s.G)), threads, smem, stream, a);

@@ -616,12 +616,8 @@ static int launch_bw_kernel(const StreamBwdArgs& a, const BwPlan& p, long blocks
     const size_t smem = lay.total() * sizeof(float);
     if (smem > 227 * 1024) return GLRGTV_ERR_UNSUPPORTED;
 #ifndef GLRGTV_EMU
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(k_stream_bwd<MODE, XW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return glr_record_launch_error();
-        configured = smem;
-    }
+    static size_t optin[GLR_MAX_DEVICES] = {0};
+    if (int rc_ = glr_smem_optin(k_stream_bwd<MODE, XW>, smem, optin)) return rc_;
 #endif
     ++g_glr_stream_launches;
     GLR_LAUNCH_FIBERS((k_stream_bwd<MODE, XW>), dim3((unsigned)blocks), p.threads, smem, stream, a);

@@ -704,12 +704,8 @@ static int launch_stream_kernel(const StreamFwdArgs& a, const StreamPlan& p, lon
     const size_t smem = lay.total() * sizeof(float);
     if (smem > 227 * 1024) return GLRGTV_ERR_UNSUPPORTED;
 #ifndef GLRGTV_EMU
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(k_stream_fwd<MODE, XW, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return glr_record_launch_error();
-        configured = smem;
-    }
+    static size_t optin[GLR_MAX_DEVICES] = {0};
+    if (int rc_ = glr_smem_optin(k_stream_fwd<MODE, XW, TMA>, smem, optin)) return rc_;
 #endif
     ++g_glr_stream_launches;
     GLR_LAUNCH_FIBERS((k_stream_fwd<MODE, XW, TMA>), dim3((unsigned)blocks), p.threads, smem, stream, a);

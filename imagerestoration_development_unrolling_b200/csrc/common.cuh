@@ -108,6 +108,20 @@ extern int g_glr_prof_on;
 #define GLR_PROF_BEGIN(slot, stream) do { if (g_glr_prof_on) glr_prof_mark((slot), 0, (stream)); } while (0)
 #define GLR_PROF_END(slot, stream) do { if (g_glr_prof_on) glr_prof_mark((slot), 1, (stream)); } while (0)
 #define GLR_CHECK_LAUNCH() glr_record_launch_error()
+// Opt a kernel into `bytes` of dynamic shared memory.  The attribute is per DEVICE, so the cache is too (a process may
+// drive several GPUs); `cache` is a function-local static array of GLR_MAX_DEVICES entries, one per kernel instantiation.
+#define GLR_MAX_DEVICES 64
+template <class K>
+static inline int glr_smem_optin(K kernel, size_t bytes, size_t* cache) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return glr_record_launch_error();
+    if (dev < 0 || dev >= GLR_MAX_DEVICES || bytes > cache[dev]) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+            return glr_record_launch_error();
+        if (dev >= 0 && dev < GLR_MAX_DEVICES) cache[dev] = bytes;
+    }
+    return 0;
+}
 static inline int glr_memset_async(void* p, int v, size_t n, cudaStream_t s) {
     return cudaMemsetAsync(p, v, n, s) == cudaSuccess ? 0 : -1;
 }

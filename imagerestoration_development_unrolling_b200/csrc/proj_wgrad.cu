@@ -98,12 +98,8 @@ extern "C" int glrgtv_proj_wgrad(int batch, int M, int N, int K, const float* gY
     if (splits < 1) splits = 1;
     const size_t smem = (size_t)2 * (WG_TM + WG_TK) * WG_P * sizeof(float);
 #ifndef GLRGTV_EMU
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_proj_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return glr_record_launch_error();
-        configured = true;
-    }
+    static size_t optin[GLR_MAX_DEVICES] = {0};
+    if (int rc_ = glr_smem_optin(k_proj_wgrad, smem, optin)) return rc_;
 #endif
     GLR_LAUNCH_FIBERS(k_proj_wgrad, dim3((unsigned)(tiles * splits)), WG_NT, smem, stream, swap ? X : gY, swap ? gY : X, gW, batch, RA, RB,
                       N, tiles_a, tiles_b, (int)splits, swap, K);
