@@ -8,8 +8,9 @@
 // the coarse term 0.25 * P^T[...] to the fine epilogue).  The coarse walker steps on even block steps only and runs
 // DF = 8 steps ahead of the fine walker, which is exactly the depth of its pipeline in fine rows.
 //
-// Eligible shapes: W % 8 == 0 and W <= 256 (a walker is at most two warps wide); everything else takes the plane
-// kernels of block_fwd.cu.
+// Eligible shapes: W % 8 == 0.  A walker is at most two warps (256 columns) wide; wider planes (4K inference) are cut
+// into column strips of STREAM_STRIP valid columns with 8 halo columns per side - the reach of the chain through the
+// half-resolution branch - whose edge lanes compute throw-away values.  Other widths take the plane kernels of block_fwd.cu.
 #include "stream.cuh"
 
 enum { MODE_BA = 0, MODE_X1 = 1, MODE_X2 = 2, MODE_X3 = 3 };
