@@ -9,6 +9,7 @@ from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGT
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--bwd", action="store_true")
+ap.add_argument("--res", type=int, default=256, help="network-input resolution (scale s runs at res >> s)")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--path", type=int, default=0)
 ap.add_argument("--scales", default="0,1,2,3")
@@ -27,7 +28,7 @@ for s, (d, g) in enumerate(zip([48, 96, 192, 384], [8, 16, 16, 32])):
         continue
     torch.manual_seed(0)
     blk = M.LocalLowpassFilteringBlock(d, 1, g).to(dev)
-    x = torch.randn(a.batch, d, 256 >> s, 256 >> s, device=dev, requires_grad=a.bwd)
+    x = torch.randn(a.batch, d, a.res >> s, a.res >> s, device=dev, requires_grad=a.bwd)
     go = torch.randn_like(x)
     def run():
         y = blk(x)
@@ -45,4 +46,4 @@ for s, (d, g) in enumerate(zip([48, 96, 192, 384], [8, 16, 16, 32])):
     ms = (ctypes.c_float * 16)(); n = (ctypes.c_int * 16)()
     lib.glrgtv_profile_read(ms, n, 16)
     out[f"scale{s}"] = {SLOTS[i]: round(ms[i] / a.reps, 3) for i in range(len(SLOTS)) if n[i]}
-print(json.dumps({"lib": os.environ.get("GLRGTV_LIB", "default"), "path": a.path, "tma": a.tma, **out}))
+print(json.dumps({"lib": os.environ.get("GLRGTV_LIB", "default"), "batch": a.batch, "res": a.res, "path": a.path, "tma": a.tma, **out}))
