@@ -24,9 +24,9 @@
 #include "stream_bwd.cuh"
 
 enum { BP_G = 0, BP_S = 1, BP_H = 2, BP_O = 3, BP_GS = 4, BP_COUNT = 5 };
-#define BW_DF 8
+#define BW_DF 6      // block steps the coarse walkers run ahead of the fine ones (the depth of their pipeline in fine rows)
 #define BW_PD 2
-#define BW_ZR 14
+#define BW_ZR 12
 #define BW_OPR 4
 #define BW_WR 4
 #define BW_MAXT 192
@@ -275,7 +275,7 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
     float stt[5] = {0.f, 0.f, 0.f, 0.f, 0.f};     // tap sums (c, R, D, U, L) of this walker's stats kernel
     float sumK = 0.f;                             // mu / ro
     float fs[4] = {0.f, 0.f, 0.f, 0.f};           // finisher: alpha_k, beta2, skip0, skip1
-    int zs = FINE ? BW_DF - 5 : 0;                // ring slot of fine row t (fine) / of fine row 2t (coarse)
+    int zs = FINE ? 3 : 0;                        // ring slot of fine row t (fine) / of fine row 2t (coarse)
 
 #pragma unroll
     for (int k = 0; k < PD; ++k) { issue(k); cp_async_commit(); }
