@@ -28,7 +28,7 @@ def slot_of(name):
         return FWD[a]
     if k == "k_stream_bwd":
         return BWD[a]
-    if k == "k_gw_stage":
+    if k in ("k_gw_stage", "k_gw_quad", "k_gw_stream"):
         return GW[a]
     if k == "k_block_stage":
         return FWD[a]
