@@ -27,8 +27,9 @@ def lib():
 
 
 # every walker width (8 / 16 / 32 / 64 lanes), partial walkers, F = 6 and 12, several channels per CTA
+# (the tall, narrow case is cut into row bands: walkers that start mid-image)
 CASES = [(48, 8, 2, 32, 256), (96, 16, 1, 20, 128), (24, 2, 1, 36, 72), (192, 16, 1, 16, 32), (12, 2, 2, 10, 8),
-         (12, 2, 1, 64, 136), (36, 3, 1, 8, 24)]
+         (12, 2, 1, 64, 136), (36, 3, 1, 8, 24), (12, 2, 1, 256, 32)]
 
 
 @pytest.mark.parametrize("case", CASES)
