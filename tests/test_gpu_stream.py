@@ -120,3 +120,29 @@ def test_4k_row_forward(M, lib):
         out = blk(x)
         assert lib.glrgtv_stream_launch_count() - n0 == 4
     assert rel(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("scale", [0, 1, 3])
+def test_backward_is_linear_in_the_output_gradient_at_benchmark_size(M, lib, scale):
+    """BASELINE config 2 shapes at the full batch of 32 (the CPU oracle is too slow there): the VJP is linear in gout -
+    gx and every parameter gradient of (a g1 + b g2) equal a * those of g1 + b * those of g2."""
+    dim, G = [48, 96, 192, 384][scale], [8, 16, 16, 32][scale]
+    H = W = 256 >> scale
+    blk = make_block(M, dim, G, random_block_state(dim, G, seed=20 + scale))
+    gen = torch.Generator(device="cuda").manual_seed(scale)
+    x = torch.randn(32, dim, H, W, device="cuda", generator=gen).requires_grad_(True)
+    g1 = torch.randn(32, dim, H, W, device="cuda", generator=gen)
+    g2 = torch.randn(32, dim, H, W, device="cuda", generator=gen)
+    out = blk(x)
+    ps = [x] + list(blk.parameters())
+    names = ["x"] + [k for k, _ in blk.named_parameters()]
+    r1 = torch.autograd.grad(out, ps, g1, retain_graph=True)
+    r2 = torch.autograd.grad(out, ps, g2, retain_graph=True)
+    r3 = torch.autograd.grad(out, ps, 0.7 * g1 - 1.3 * g2)
+    for n, a, b, c in zip(names, r1, r2, r3):
+        ref = 0.7 * a - 1.3 * b
+        if float(ref.abs().max()) == 0.0:
+            assert float(c.abs().max()) == 0.0, n
+        else:
+            assert rel(c, ref) < 2e-4, (n, rel(c, ref))
+    assert torch.isfinite(out).all()
