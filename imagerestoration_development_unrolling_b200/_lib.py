@@ -99,6 +99,7 @@ _SIGS = {
     "glrgtv_pool2_fwd": (C.c_int, [_P(Shape), fp, fp, fp]),
     "glrgtv_unpool2_fwd": (C.c_int, [_P(Shape), fp, fp, fp]),
     "glrgtv_proj_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]),
+    "glrgtv_space_to_depth": (C.c_int, [C.c_int, C.c_long, C.c_int, C.c_int, fp, fp, fp]),
     "glrgtv_proj_wgrad": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]),
     "glrgtv_block_fwd": (C.c_int, [_P(Shape), _P(BlockParams), fp, fp, fp, fp, _P(BlockSaved), fp]),
     "glrgtv_block_bwd_workspace_bytes": (C.c_size_t, [_P(Shape)]),

@@ -164,3 +164,47 @@ int glrgtv_check_device(void) {
 }
 }
 #endif
+
+#ifndef GLRGTV_EMU
+// ---- space-to-depth / depth-to-space of the 2x2 stride-2 projection (patchs_features_extraction01[0], V1X0:593-603):
+// out[b, c*4 + dy*2 + dx, h', w'] = x[b, c, 2h'+dy, 2w'+dx]  (torch pixel_unshuffle order).  torch's permute-copy kernel
+// is uncoalesced (0.4 ms for the scale-0 map); here a thread moves a 2 x 8 block with float4 loads and stores.
+__global__ void __launch_bounds__(256) k_space_to_depth(const float* __restrict__ x, float* __restrict__ y, long planes, int H, int W,
+                                                       int inverse) {
+    const int Hc = H / 2, Wc = W / 2, Q = Wc / 4;                    // Q: groups of 4 coarse (8 fine) columns per row
+    const long total = planes * Hc * Q;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % Q), hc = (int)((i / Q) % Hc);
+        const long pl = i / ((long)Q * Hc);
+        float* fine = const_cast<float*>(inverse ? y : x) + (pl * H + 2 * hc) * W + 8 * q;          // the full-resolution tensor
+        float* deep = const_cast<float*>(inverse ? x : y) + ((pl * 4) * Hc + hc) * (long)Wc + 4 * q;  // plane c*4 of the deep tensor
+        const long ps = (long)Hc * Wc;
+        if (!inverse) {
+            const float4 a0 = *reinterpret_cast<const float4*>(fine), a1 = *reinterpret_cast<const float4*>(fine + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(fine + W), b1 = *reinterpret_cast<const float4*>(fine + W + 4);
+            *reinterpret_cast<float4*>(deep) = make_float4(a0.x, a0.z, a1.x, a1.z);
+            *reinterpret_cast<float4*>(deep + ps) = make_float4(a0.y, a0.w, a1.y, a1.w);
+            *reinterpret_cast<float4*>(deep + 2 * ps) = make_float4(b0.x, b0.z, b1.x, b1.z);
+            *reinterpret_cast<float4*>(deep + 3 * ps) = make_float4(b0.y, b0.w, b1.y, b1.w);
+        } else {
+            const float4 d0 = *reinterpret_cast<const float4*>(deep), d1 = *reinterpret_cast<const float4*>(deep + ps);
+            const float4 d2 = *reinterpret_cast<const float4*>(deep + 2 * ps), d3 = *reinterpret_cast<const float4*>(deep + 3 * ps);
+            *reinterpret_cast<float4*>(fine) = make_float4(d0.x, d1.x, d0.y, d1.y);
+            *reinterpret_cast<float4*>(fine + 4) = make_float4(d0.z, d1.z, d0.w, d1.w);
+            *reinterpret_cast<float4*>(fine + W) = make_float4(d2.x, d3.x, d2.y, d3.y);
+            *reinterpret_cast<float4*>(fine + W + 4) = make_float4(d2.z, d3.z, d2.w, d3.w);
+        }
+    }
+}
+
+// inverse == 0: x [planes,H,W] -> y [planes*4,H/2,W/2];  inverse == 1: x [planes*4,H/2,W/2] -> y [planes,H,W].  W % 8 == 0, H even.
+extern "C" int glrgtv_space_to_depth(int inverse, long planes, int H, int W, const float* x, float* y, void* stream) {
+    if (planes <= 0 || H <= 0 || W <= 0 || (H & 1)) return GLRGTV_ERR_SHAPE;
+    if (W % 8) return GLRGTV_ERR_UNSUPPORTED;
+    if (!x || !y || (((uintptr_t)x | (uintptr_t)y) & 15u)) return GLRGTV_ERR_POINTER;
+    const long total = planes * (H / 2) * (W / 8);
+    const long blocks = (total + 255) / 256;
+    GLR_LAUNCH(k_space_to_depth, dim3((unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks)), 256, 0, stream, x, y, planes, H, W, inverse);
+    return GLR_CHECK_LAUNCH();
+}
+#endif

@@ -184,7 +184,8 @@ class MixtureGTVGLR(nn.Module):
         else:
             mm = ops.projection                       # cuBLAS fp32 forward / input gradient, split-reduction weight gradient
         feat0 = mm(w00, patchs.reshape(b, c, h * w)).reshape(b, 2 * c, h, w)
-        xs = nn.functional.pixel_unshuffle(patchs, 2).reshape(b, 4 * c, (h // 2) * (w // 2))
+        s2d = ops.space_to_depth(patchs, False) if w % 8 == 0 else nn.functional.pixel_unshuffle(patchs, 2)
+        xs = s2d.reshape(b, 4 * c, (h // 2) * (w // 2))
         feat1 = mm(w01b, mm(w01a, xs)).reshape(b, 2 * c, h // 2, w // 2)
         return feat0, feat1
 

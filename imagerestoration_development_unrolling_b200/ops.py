@@ -430,6 +430,35 @@ def _pg_backward(ctx, gy):
 proj_gemm.register_autograd(_pg_backward, setup_context=_pg_setup)
 
 
+# ---- space-to-depth in front of the 2x2 stride-2 projection (torch.pixel_unshuffle order), and its inverse
+@torch.library.custom_op(f"{_NS}::space_to_depth", mutates_args=())
+def space_to_depth(x: Tensor, inverse: bool) -> Tensor:
+    """x [B,C,H,W] -> [B,4C,H/2,W/2]   (inverse: [B,4C,h,w] -> [B,C,2h,2w]); glrgtv_space_to_depth"""
+    _chk(x)
+    x = _c(x)
+    B, C, H, W = x.shape
+    if inverse:
+        y = x.new_empty(B, C // 4, 2 * H, 2 * W)
+        _call("glrgtv_space_to_depth", x, 1, B * (C // 4), 2 * H, 2 * W, x, y)
+    else:
+        y = x.new_empty(B, 4 * C, H // 2, W // 2)
+        _call("glrgtv_space_to_depth", x, 0, B * C, H, W, x, y)
+    return y
+
+
+@space_to_depth.register_fake
+def _(x, inverse):
+    B, C, H, W = x.shape
+    return x.new_empty(B, C // 4, 2 * H, 2 * W) if inverse else x.new_empty(B, 4 * C, H // 2, W // 2)
+
+
+def _s2d_setup(ctx, inputs, output):
+    ctx.inverse = inputs[1]
+
+
+space_to_depth.register_autograd(lambda ctx, g: (space_to_depth(g, not ctx.inverse), None), setup_context=_s2d_setup)
+
+
 # ---- projection with a library forward / input gradient and the split-reduction weight-gradient kernel
 def proj_wgrad_supported(M: int, K: int, N: int) -> bool:
     return N % 32 == 0 and ((M % 96 == 0 and K % 48 == 0) or (K % 96 == 0 and M % 48 == 0))

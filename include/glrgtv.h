@@ -243,6 +243,11 @@ int glrgtv_proj_gemm(int transpose_w, int batch, int M, int N, int K, const floa
  * K % 48 == 0) or (K % 96 == 0, M % 48 == 0); GLRGTV_ERR_UNSUPPORTED otherwise. */
 int glrgtv_proj_wgrad(int batch, int M, int N, int K, const float* gY, const float* X, float* gW, void* stream);
 
+/* Space-to-depth in front of the 2x2 stride-2 projection (patchs_features_extraction01[0], V1X0:593-603) and its inverse:
+ * inverse == 0: x [planes,H,W] -> y [planes*4,H/2,W/2], y[p*4 + dy*2 + dx, h, w] = x[p, 2h+dy, 2w+dx] (pixel_unshuffle order);
+ * inverse == 1: the other way round (x is the deep tensor).  `planes` = B*C; W % 8 == 0, H even, 16-byte aligned. */
+int glrgtv_space_to_depth(int inverse, long planes, int H, int W, const float* x, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,3 +160,15 @@ def test_projection_weight_gradient_kernel(shape):
     assert rel(y, torch.einsum("mk,bkn->bmn", w64, x64)) < 2e-6
     assert rel(gx, torch.einsum("mk,bmn->bkn", w64, gy64)) < 2e-6
     assert rel(gw, torch.einsum("bmn,bkn->mk", gy64, x64)) < 5e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 6, 8, 16), (1, 48, 64, 256), (3, 5, 2, 8)])
+def test_space_to_depth_matches_pixel_unshuffle(shape):
+    from imagerestoration_development_unrolling_b200 import ops
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(1)).cuda().requires_grad_(True)
+    y = ops.space_to_depth(x, False)
+    ref = torch.nn.functional.pixel_unshuffle(x, 2)
+    assert torch.equal(y, ref)
+    g = torch.randn_like(ref)
+    assert torch.equal(torch.autograd.grad(y, x, g)[0], torch.nn.functional.pixel_shuffle(g, 2))
+    assert torch.equal(ops.space_to_depth(y.detach(), True), x.detach())
