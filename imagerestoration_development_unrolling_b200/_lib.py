@@ -102,6 +102,7 @@ _SIGS = {
     "glrgtv_space_to_depth": (C.c_int, [C.c_int, C.c_long, C.c_int, C.c_int, fp, fp, fp]),
     "glrgtv_proj_wgrad": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]),
     "glrgtv_block_fwd": (C.c_int, [_P(Shape), _P(BlockParams), fp, fp, fp, fp, _P(BlockSaved), fp]),
+    "glrgtv_block_fwd_stage": (C.c_int, [C.c_int, _P(Shape), _P(BlockParams), fp, fp, fp, fp, _P(BlockSaved), C.c_int, C.c_int, fp]),
     "glrgtv_block_bwd_workspace_bytes": (C.c_size_t, [_P(Shape)]),
     "glrgtv_block_bwd": (C.c_int, [_P(Shape), _P(BlockParams), fp, fp, fp, _P(BlockSaved), fp, fp, fp, fp,
                                    _P(BlockGrads), fp, C.c_size_t, fp]),

@@ -398,6 +398,38 @@ int glr_launch_gtv_coeffs(const glrgtv_shape& s, const float* w, float* c, void*
 int glr_stream_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, const float* x, float* out,
                          const glrgtv_block_saved* sv, void* stream);
 
+int glr_stream_block_fwd_stage(int stage, const glrgtv_shape* s, const glrgtv_block_params* p, const float* x, float* out,
+                               const glrgtv_block_saved* sv, int row0, int row1, void* stream);
+
+// One piece of the block forward, for callers that interleave the stages with their own work (spatially sharded
+// inference: a halo exchange between stages).  stage 0 = edge weights + GTV coefficients of the WHOLE local plane;
+// stages 1..4 = BA, X1, X2, X3 on the rows [row0, row1).  Streaming kernels only (W % 8 == 0).
+extern "C" int glrgtv_block_fwd_stage(int stage, const glrgtv_shape* s, const glrgtv_block_params* p, const float* x,
+                                      const float* feat0, const float* feat1, float* out, const glrgtv_block_saved* sv,
+                                      int row0, int row1, void* stream) {
+    if (!glr_shape_ok(s) || (s->H & 1) || (s->W & 1)) return GLRGTV_ERR_SHAPE;
+    int rc = glr_block_params_ok(s, p);
+    if (rc) return rc;
+    if (!sv || !glr_stream_fwd_eligible(s)) return GLRGTV_ERR_UNSUPPORTED;
+    float* need[11] = {sv->wT0, sv->wL0, sv->wT1, sv->wL1, sv->bA, sv->x1, sv->bB, sv->r1, sv->x2, sv->cT0, sv->cT1};
+    for (int i = 0; i < 11; ++i)
+        if (!glr_aligned(need[i]) || !glr_aligned16(need[i])) return GLRGTV_ERR_POINTER;
+    GLR_REQUIRE_PTR(x);
+    if (!glr_aligned16(x)) return GLRGTV_ERR_POINTER;
+    if (stage == 0) {
+        GLR_REQUIRE_PTR(feat0); GLR_REQUIRE_PTR(feat1);
+        glrgtv_shape sc = *s;
+        sc.H /= 2; sc.W /= 2;
+        if ((rc = launch_weights(*s, feat0, p->gtv0.multiM, p->glr0.multiM, sv->wT0, sv->wL0, stream))) return rc;
+        if ((rc = launch_weights(sc, feat1, p->gtv1.multiM, p->glr1.multiM, sv->wT1, sv->wL1, stream))) return rc;
+        if ((rc = glr_launch_gtv_coeffs(*s, sv->wT0, sv->cT0, stream))) return rc;
+        return glr_launch_gtv_coeffs(sc, sv->wT1, sv->cT1, stream);
+    }
+    if (stage < 1 || stage > 4 || row0 < 0 || row1 > s->H || row0 >= row1 || (row0 & 1) || (row1 & 1)) return GLRGTV_ERR_SHAPE;
+    if (stage == 4) { GLR_REQUIRE_PTR(out); if (!glr_aligned16(out)) return GLRGTV_ERR_POINTER; }
+    return glr_stream_block_fwd_stage(stage - 1, s, p, x, out, sv, row0, row1, stream);
+}
+
 extern "C" int glrgtv_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, const float* x,
                                 const float* feat0, const float* feat1, float* out, const glrgtv_block_saved* sv,
                                 void* stream) {

@@ -32,6 +32,7 @@ struct StreamFwdArgs {
     int nch;        // channels per CTA (divides F)
     int band_rows;  // fine rows per CTA (even)
     int n_bands;
+    int row_base, row_end;   // the rows this launch produces: [row_base, row_end) (even bounds; the whole plane by default)
     int n_strips;   // column strips (planes wider than a 64-lane walker): STREAM_STRIP valid columns each, 8 columns of halo per side
 };
 
@@ -104,8 +105,8 @@ __device__ __forceinline__ StreamCta stream_cta(const StreamFwdArgs& a, int GL) 
     const int chunk = bid % chunks; bid /= chunks;
     c.g = bid % c.G; c.b = bid / c.G;
     c.f0 = chunk * c.nch;
-    c.R0 = band * a.band_rows;
-    c.R1 = c.R0 + a.band_rows < c.H ? c.R0 + a.band_rows : c.H;
+    c.R0 = a.row_base + band * a.band_rows;
+    c.R1 = c.R0 + a.band_rows < a.row_end ? c.R0 + a.band_rows : a.row_end;
     c.K0 = c.R0 / 2;
     c.M = (c.R1 - c.R0) + 6 + STREAM_DF;
     if (a.n_strips > 1) {
@@ -670,7 +671,7 @@ int glr_stream_fwd_eligible(const glrgtv_shape* s) {
 struct StreamPlan {
     int GL, nch, threads, band_rows, n_bands, n_strips;
 };
-static StreamPlan stream_plan(const glrgtv_shape& s) {
+static StreamPlan stream_plan(const glrgtv_shape& s, int rows) {
     StreamPlan p;
     p.GL = s.W > 128 ? 64 : s.W > 64 ? 32 : s.W > 32 ? 16 : 8;
     p.n_strips = s.W > 256 ? (s.W + STREAM_STRIP - 1) / STREAM_STRIP : 1;
@@ -684,9 +685,9 @@ static StreamPlan stream_plan(const glrgtv_shape& s) {
     // whole-height bands unless the grid would leave SMs idle
     const long ctas = (long)s.B * s.G * (s.F / p.nch) * p.n_strips;
     int bands = 1;
-    while (ctas * bands < 592 && s.H / (bands * 2) >= 64) bands *= 2;
-    p.band_rows = ((s.H + bands - 1) / bands + 1) & ~1;
-    p.n_bands = (s.H + p.band_rows - 1) / p.band_rows;
+    while (ctas * bands < 592 && rows / (bands * 2) >= 64) bands *= 2;
+    p.band_rows = ((rows + bands - 1) / bands + 1) & ~1;
+    p.n_bands = (rows + p.band_rows - 1) / p.band_rows;
     return p;
 }
 
@@ -715,7 +716,7 @@ static int launch_stream_kernel(const StreamFwdArgs& a, const StreamPlan& p, lon
 template <int MODE>
 static int launch_stream_stage(StreamFwdArgs a, void* stream) {
     const glrgtv_shape& s = a.s;
-    const StreamPlan p = stream_plan(s);
+    const StreamPlan p = stream_plan(s, a.row_end - a.row_base);
     a.nch = p.nch; a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.n_strips = p.n_strips;
     const long blocks = (long)s.B * s.G * (s.F / p.nch) * p.n_bands * p.n_strips;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
@@ -752,7 +753,7 @@ int glr_stream_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, co
     a.s = *s; a.p = *p;
     a.wT0 = sv->wT0; a.wL0 = sv->wL0; a.wT1 = sv->wT1; a.wL1 = sv->wL1; a.cT0 = sv->cT0; a.cT1 = sv->cT1;
     a.y = nullptr; a.bB_in = nullptr; a.r1_in = nullptr; a.out1 = nullptr; a.out2 = nullptr;
-    a.nch = 1; a.band_rows = s->H; a.n_bands = 1; a.n_strips = 1;
+    a.nch = 1; a.band_rows = s->H; a.n_bands = 1; a.n_strips = 1; a.row_base = 0; a.row_end = s->H;
     a.z = x; a.out0 = sv->bA;
     if ((rc = launch_stream_stage<MODE_BA>(a, stream))) return rc;
     a.z = sv->bA; a.out0 = sv->x1;
@@ -761,4 +762,23 @@ int glr_stream_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, co
     if ((rc = launch_stream_stage<MODE_X2>(a, stream))) return rc;
     a.z = sv->x2; a.y = x; a.bB_in = sv->bB; a.r1_in = sv->r1; a.out0 = out; a.out1 = nullptr; a.out2 = nullptr;
     return launch_stream_stage<MODE_X3>(a, stream);
+}
+
+// One solver stage on the rows [row0, row1) of the plane (even bounds).  The rows outside the range must already hold
+// valid data in the stage's inputs wherever the chain reaches them (8 rows on either side, see glrgtv.h): this is what a
+// spatially sharded caller exchanges between stages.
+int glr_stream_block_fwd_stage(int stage, const glrgtv_shape* s, const glrgtv_block_params* p, const float* x, float* out,
+                               const glrgtv_block_saved* sv, int row0, int row1, void* stream) {
+    StreamFwdArgs a;
+    a.s = *s; a.p = *p;
+    a.wT0 = sv->wT0; a.wL0 = sv->wL0; a.wT1 = sv->wT1; a.wL1 = sv->wL1; a.cT0 = sv->cT0; a.cT1 = sv->cT1;
+    a.y = nullptr; a.bB_in = nullptr; a.r1_in = nullptr; a.out1 = nullptr; a.out2 = nullptr;
+    a.nch = 1; a.band_rows = s->H; a.n_bands = 1; a.n_strips = 1; a.row_base = row0; a.row_end = row1;
+    switch (stage) {
+        case MODE_BA: a.z = x; a.out0 = sv->bA; return launch_stream_stage<MODE_BA>(a, stream);
+        case MODE_X1: a.z = sv->bA; a.out0 = sv->x1; return launch_stream_stage<MODE_X1>(a, stream);
+        case MODE_X2: a.z = sv->x1; a.y = x; a.out0 = sv->x2; a.out1 = sv->bB; a.out2 = sv->r1; return launch_stream_stage<MODE_X2>(a, stream);
+        case MODE_X3: a.z = sv->x2; a.y = x; a.bB_in = sv->bB; a.r1_in = sv->r1; a.out0 = out; return launch_stream_stage<MODE_X3>(a, stream);
+    }
+    return GLRGTV_ERR_UNSUPPORTED;
 }

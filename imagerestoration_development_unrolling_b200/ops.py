@@ -646,3 +646,20 @@ lowpass_block_fwd.register_autograd(_lb_backward, setup_context=_lb_setup)
 def lowpass_block(x: Tensor, feat0: Tensor, feat1: Tensor, params: Sequence[Tensor], n_graphs: int) -> Tensor:
     """LocalLowpassFilteringBlock / MixtureGTVGLR forward (V1X0:707-811, 985-988) as one differentiable op."""
     return lowpass_block_fwd(x, feat0, feat1, list(params), n_graphs)[0]
+
+
+def lowpass_block_stage(stage: int, x: Tensor, feat0, feat1, params: Sequence[Tensor], n_graphs: int, saved: Sequence[Tensor],
+                        out: Tensor, row0: int, row1: int) -> None:
+    """One piece of the block forward (glrgtv_block_fwd_stage; inference only, no autograd): stage 0 = edge weights and GTV
+    coefficients of the whole plane, 1..4 = BA, X1, X2, X3 on the rows [row0, row1).  `saved` is the list lowpass_block_fwd
+    returns after `out` (allocated by the caller: see shard.sharded_block_forward_staged)."""
+    _chk(x, out, *params, *saved)
+    B, G, F, H, W = _block_geometry(x, n_graphs)
+    sv = L.BlockSaved(*[t.data_ptr() for t in saved])
+    _call("glrgtv_block_fwd_stage", x, int(stage), L.make_shape(B, G, F, H, W), _block_structs([_c(p) for p in params]), x,
+          feat0, feat1, out, sv, int(row0), int(row1))
+
+
+def alloc_block_saved(x: Tensor, n_graphs: int) -> List[Tensor]:
+    B, G, F, H, W = _block_geometry(x, n_graphs)
+    return [x.new_empty(s) for s in _saved_shapes(B, G, F, H, W)]

@@ -16,6 +16,7 @@ import torch
 import torch.distributed as dist
 
 BLOCK_HALO_ROWS = 26
+STAGE_HALO_ROWS = 8     # reach of ONE solver stage: 3 rows at full resolution, 3 coarse rows = 6 through the half-resolution branch, even
 
 
 # ----------------------------------------------------------------------------------------------- training
@@ -96,3 +97,55 @@ def sharded_block_forward(block: Callable[[torch.Tensor], torch.Tensor], strip: 
     ext, t, b = exchange_row_halos(strip, halo, rank, world, group)
     out = block(ext)
     return out[..., t:out.shape[-2] - b, :].contiguous() if (t or b) else out
+
+
+def exchange_row_halos_inplace(buf: torch.Tensor, top: int, bot: int, rank: int, world: int, group=None) -> None:
+    """buf [B,C,top+h+bot,W] holds this rank's h rows between halo rows that belong to the neighbours: send the first `top`
+    / last `bot` OWN rows up / down and receive the neighbours' rows into the halo rows (top / bot are 0 at the image border)."""
+    ops, keep = [], []
+    H = buf.shape[-2]
+    if top:
+        send = buf[..., top:2 * top, :].contiguous()
+        recv = torch.empty_like(send)
+        keep.append((recv, slice(0, top)))
+        ops += [dist.P2POp(dist.isend, send, rank - 1, group), dist.P2POp(dist.irecv, recv, rank - 1, group)]
+    if bot:
+        send = buf[..., H - 2 * bot:H - bot, :].contiguous()
+        recv = torch.empty_like(send)
+        keep.append((recv, slice(H - bot, H)))
+        ops += [dist.P2POp(dist.isend, send, rank + 1, group), dist.P2POp(dist.irecv, recv, rank + 1, group)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for recv, rows in keep:
+            buf[..., rows, :] = recv
+
+
+@torch.no_grad()
+def sharded_block_forward_staged(blk, strip: torch.Tensor, rank: int, world: int, group=None) -> torch.Tensor:
+    """LocalLowpassFilteringBlock on this rank's row strip with ONE 8-row halo exchange PER SOLVER STAGE instead of one
+    26-row exchange per block: x, bA, x1 and x2 are exchanged, every stage computes exactly the rank's own rows
+    (glrgtv_block_fwd_stage), so nothing but the edge weights of the 8 halo rows is computed twice.  Exact: a stage reaches
+    at most 7 rows beyond the rows it produces.  `blk` is the drop-in module (its streaming kernels: W % 8 == 0)."""
+    from . import ops
+    if world == 1:
+        return blk(strip)
+    if strip.shape[-2] < 2 * STAGE_HALO_ROWS:
+        raise ValueError(f"strip of {strip.shape[-2]} rows is too thin for two {STAGE_HALO_ROWS}-row halos")
+    ext, t, b = exchange_row_halos(strip, STAGE_HALO_ROWS, rank, world, group)
+    ext = ext.contiguous()
+    lf = blk.local_filter
+    feat0, feat1 = lf._projections(ext)                   # per-pixel / 2x2-aligned: valid on the halo rows too
+    params = lf._block_params() + [blk.skip_weight]
+    saved = ops.alloc_block_saved(ext, lf.n_graphs)
+    names = dict(zip(ops._SAVED, saved))
+    out = torch.empty_like(ext)
+    H = ext.shape[-2]
+    r0, r1 = t, H - b
+    ops.lowpass_block_stage(0, ext, feat0.contiguous(), feat1.contiguous(), params, lf.n_graphs, saved, out, 0, H)
+    for stage, produced in ((1, "bA"), (2, "x1"), (3, "x2")):
+        ops.lowpass_block_stage(stage, ext, None, None, params, lf.n_graphs, saved, out, r0, r1)
+        buf = names[produced].view(ext.shape)             # [B,G,F,H,W] -> [B,C,H,W]
+        exchange_row_halos_inplace(buf, t, b, rank, world, group)
+    ops.lowpass_block_stage(4, ext, None, None, params, lf.n_graphs, saved, out, r0, r1)
+    return out[..., r0:r1, :].contiguous()

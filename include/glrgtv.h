@@ -222,6 +222,16 @@ int glrgtv_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, const 
                      const float* feat0, const float* feat1, float* out, const glrgtv_block_saved* saved,
                      void* stream);
 
+/* The same forward, one piece at a time, for callers that interleave the pieces with their own work - spatially sharded
+ * inference exchanges halo rows between stages (shard.py).  stage 0: edge weights and GTV coefficients of the whole local
+ * plane (needs feat0 / feat1); stages 1..4: BA (x -> saved.bA), X1 (bA -> x1), X2 (x1, x -> x2, bB, r1), X3 (x2, bB, r1,
+ * x -> out) on the rows [row0, row1) only (even bounds).  A stage reads its stencil input (x | bA | x1 | x2) and the weights
+ * up to 8 rows outside [row0, row1): those rows must hold valid data, or lie outside the plane (then the reference's border
+ * rules apply).  Streaming kernels only: W % 8 == 0, else GLRGTV_ERR_UNSUPPORTED. */
+int glrgtv_block_fwd_stage(int stage, const glrgtv_shape* s, const glrgtv_block_params* p, const float* x,
+                           const float* feat0, const float* feat1, float* out, const glrgtv_block_saved* saved,
+                           int row0, int row1, void* stream);
+
 size_t glrgtv_block_bwd_workspace_bytes(const glrgtv_shape* s);
 /* gout [B,C,H,W] -> gx [B,C,H,W] (the direct path, WITHOUT the feature-path term),
  * gfeat0 [B,2C,H,W], gfeat1 [B,2C,H/2,W/2] (for the caller's GEMM backward), and parameter grads. */

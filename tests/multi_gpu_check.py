@@ -43,6 +43,15 @@ def main():
     if rank == 0:
         print(f"sharded inference, {world} strips of a {H}x{W} map: max rel err vs single GPU = {float(t):.2e}")
     assert float(t) < 1e-6
+    # (1b) the same with one 8-row exchange per solver stage (no redundant rows)
+    with torch.no_grad():
+        mine = shard.sharded_block_forward_staged(blk, x[:, :, a:b].contiguous(), rank, world)
+    err = float((mine - full[:, :, a:b]).abs().max() / full.abs().max())
+    t = torch.tensor([err], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"staged sharded inference (8-row exchange per stage), {world} strips: max rel err vs single GPU = {float(t):.2e}")
+    assert float(t) < 1e-6
 
     # (2) batch-sharded gradients
     xb = torch.randn(2 * world, 48, 64, 64, generator=gen).to(dev)

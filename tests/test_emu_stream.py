@@ -87,3 +87,32 @@ def test_stream_block_backward(case, gw_streaming):
     E.emu_lib().glrgtv_set_gw_kernel(0)
     bad = {k: v for k, v in errs.items() if v > 2e-4}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("case", [(12, 2, 1, 40, 16), (6, 1, 2, 64, 24), (4, 2, 1, 24, 272)])
+def test_stage_entry_point_on_row_ranges(case):
+    """glrgtv_block_fwd_stage: the block forward as weights + four stages, every stage run on three row ranges in turn
+    (what a spatially sharded caller does between halo exchanges) equals the oracle"""
+    dim, G, B, H, W = case
+    F = dim // G
+    sd = random_block_state(dim, G, seed=500 + H)
+    x = torch.randn(B, dim, H, W, generator=torch.Generator().manual_seed(H + W))
+    ref_out, inter = O.mixture_gtvglr_forward({k: v.double() for k, v in sd.items()}, x.double(), "local_filter.",
+                                              return_intermediates=True)
+    s = sd["skip_weight"].double()
+    ref_out = s[0] * x.double() + s[1] * ref_out
+    f0, f1 = oracle_features(sd, x)
+    p, keep = block_structs(sd)
+    sv, saved = alloc_saved(B, G, F, H, W)
+    for t in saved.values():
+        t.fill_(float("nan"))                      # a stage that reads rows nobody produced shows up as NaN
+    out = torch.full_like(x, float("nan"))
+    shp = L.make_shape(B, G, F, H, W)
+    E.call("glrgtv_block_fwd_stage", 0, shp, p, x, f0, f1, out, sv, 0, H, None)
+    cuts = [0, (H // 3) & ~1, (2 * H // 3) & ~1, H]
+    for stage in (1, 2, 3, 4):
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            E.call("glrgtv_block_fwd_stage", stage, shp, p, x, None, None, out, sv, a, b, None)
+    for n in ("bA", "x1", "bB", "r1", "x2"):
+        assert rel(saved[n], inter[n]) < 2e-5, (n, rel(saved[n], inter[n]))
+    assert rel(out, ref_out) < 1e-5

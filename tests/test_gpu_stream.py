@@ -146,3 +146,45 @@ def test_backward_is_linear_in_the_output_gradient_at_benchmark_size(M, lib, sca
         else:
             assert rel(c, ref) < 2e-4, (n, rel(c, ref))
     assert torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_staged_strips_equal_the_whole_plane(M, lib, world):
+    """shard.sharded_block_forward_staged's algorithm in ONE process: `world` row strips with 8-row halos, every solver
+    stage on the strip's own rows only (ops.lowpass_block_stage), halo rows of x / bA / x1 / x2 copied between the strips'
+    buffers where NCCL would exchange them.  Must reproduce the whole-plane result exactly."""
+    from imagerestoration_development_unrolling_b200 import ops, shard
+    dim, G, H, W = 48, 8, 96, 64
+    blk = make_block(M, dim, G, random_block_state(dim, G, seed=31))
+    x = torch.randn(1, dim, H, W, generator=torch.Generator().manual_seed(8)).cuda()
+    lf = blk.local_filter
+    hr = shard.STAGE_HALO_ROWS
+    with torch.no_grad():
+        full = blk(x)
+        bounds = shard.strip_bounds(H, world, align=2)
+        st = []
+        for r, (a, b) in enumerate(bounds):
+            t, bt = (hr if r > 0 else 0), (hr if r < world - 1 else 0)
+            ext = x[:, :, a - t:b + bt].contiguous()
+            f0, f1 = lf._projections(ext)
+            saved = ops.alloc_block_saved(ext, G)
+            for s_ in saved:
+                s_.fill_(float("nan"))
+            out = torch.full_like(ext, float("nan"))
+            params = lf._block_params() + [blk.skip_weight]
+            ops.lowpass_block_stage(0, ext, f0.contiguous(), f1.contiguous(), params, G, saved, out, 0, ext.shape[-2])
+            st.append(dict(ext=ext, saved=dict(zip(ops._SAVED, saved)), out=out, params=params, t=t, b=bt, list=saved))
+        for stage, produced in ((1, "bA"), (2, "x1"), (3, "x2"), (4, None)):
+            for s in st:
+                Hs = s["ext"].shape[-2]
+                ops.lowpass_block_stage(stage, s["ext"], None, None, s["params"], G, s["list"], s["out"], s["t"], Hs - s["b"])
+            if produced:
+                bufs = [s["saved"][produced].view(s["ext"].shape) for s in st]
+                for r in range(world - 1):              # rank r's last own rows -> rank r+1's top halo, and back
+                    up, dn = bufs[r], bufs[r + 1]
+                    Hu = up.shape[-2]
+                    dn[..., :hr, :] = up[..., Hu - 2 * hr:Hu - hr, :]
+                    up[..., Hu - hr:, :] = dn[..., hr:2 * hr, :]
+        got = torch.cat([s["out"][..., s["t"]:s["out"].shape[-2] - s["b"], :] for s in st], dim=-2)
+    assert torch.isfinite(got).all()
+    assert rel(got, full) < 1e-6, rel(got, full)

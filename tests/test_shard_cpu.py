@@ -107,3 +107,31 @@ def test_halo_must_cover_the_receptive_radius():
         out = O.lowpass_block_forward(sd, x[:, :, :40 + halo])[:, :, :40]
         errs[halo] = float((out - full[:, :, :40]).abs().max())
     assert errs[8] > 1e-9 and errs[26] < 1e-14, errs
+
+
+def _inplace_worker(rank, world, port, q):
+    _init(rank, world, port)
+    h, halo = 6, 2
+    top, bot = (halo if rank > 0 else 0), (halo if rank < world - 1 else 0)
+    buf = torch.full((1, 2, top + h + bot, 3), float("nan"))
+    # own rows hold their global row index (rank * h + local row)
+    buf[..., top:top + h, :] = (rank * h + torch.arange(h, dtype=torch.float32)).view(1, 1, h, 1)
+    shard.exchange_row_halos_inplace(buf, top, bot, rank, world)
+    q.put((rank, buf[0, 0, :, 0].numpy().copy(), top))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_inplace_halo_exchange(world):
+    """after the exchange every buffer row (own or halo) holds its global row index"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_inplace_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(60) for p in procs]
+    for rank, rows, top in res:
+        first = rank * 6 - top
+        assert rows.tolist() == [float(first + i) for i in range(len(rows))], (rank, rows)
