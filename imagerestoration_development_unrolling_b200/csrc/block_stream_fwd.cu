@@ -3,10 +3,11 @@
 //
 // One CTA = one (batch, graph), `nch` of its channels, a band of rows.  Per channel there is a FINE walker (GL lanes,
 // the full-resolution chain and the stage epilogue) and a COARSE walker (GL/2 lanes, the half-resolution chain on the
-// 2x2 mean of the input).  Both run the SAME step code on the same register state; they differ in how a row is
+// 2x2 mean of the input).  Both are instantiations of ONE step template (stream_walk); they differ in how a row is
 // loaded (direct / pooled) and where the finished row goes (global memory / a two-slot shared-memory ring that hands
 // the coarse term 0.25 * P^T[...] to the fine epilogue).  The coarse walker steps on even block steps only and runs
-// DF = 8 steps ahead of the fine walker, which is exactly the depth of its pipeline in fine rows.
+// DF = 8 steps ahead of the fine walker, which is exactly the depth of its pipeline in fine rows.  A launch may be
+// restricted to a row range of the plane (glrgtv_block_fwd_stage): walkers then start mid-image on real rows.
 //
 // Eligible shapes: W % 8 == 0.  A walker is at most two warps (256 columns) wide; wider planes (4K inference) are cut
 // into column strips of STREAM_STRIP valid columns with 8 halo columns per side - the reach of the chain through the
