@@ -769,7 +769,7 @@ extern "C" size_t glrgtv_block_bwd_workspace_bytes(const glrgtv_shape* s) {
 int glr_block_params_ok(const glrgtv_shape* s, const glrgtv_block_params* p);
 // block_stream_fwd.cu
 extern int g_glr_block_path;
-int glr_stream_eligible(const glrgtv_shape* s);
+int glr_stream_fwd_eligible(const glrgtv_shape* s);
 #ifndef GLR_STREAM_BWD_MIN_W
 #define GLR_STREAM_BWD_MIN_W 8      // narrower planes take the plane kernels in automatic mode
 #endif
@@ -799,13 +799,13 @@ extern "C" int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params
     float* ws = (float*)workspace;
     const size_t N = (size_t)s->B * s->H * s->W, GE = (size_t)s->G * 4;
     // register-streaming backward (block_stream_bwd.cu + block_gw.cu) where the shape allows, else the plane kernels
-    const bool can_stream = glr_stream_eligible(s) && sv->cT0 && sv->cT1;
+    const bool can_stream = glr_stream_fwd_eligible(s) && sv->cT0 && sv->cT1;     // any W % 8 == 0: wide planes in column strips
     if (g_glr_block_path == 2 && !can_stream) return GLRGTV_ERR_UNSUPPORTED;
     if (can_stream && g_glr_block_path != 1 && (g_glr_block_path == 2 || s->W >= GLR_STREAM_BWD_MIN_W)) {
         StreamBwdArgs b;
         b.s = *s; b.p = *p; b.gr = *gr;
         b.wT0 = sv->wT0; b.wL0 = sv->wL0; b.wT1 = sv->wT1; b.wL1 = sv->wL1; b.cT0 = sv->cT0; b.cT1 = sv->cT1;
-        b.nch = 1; b.band_rows = s->H; b.n_bands = 1;
+        b.nch = 1; b.band_rows = s->H; b.n_bands = 1; b.n_strips = 1;
         GwArgs w;
         w.s = *s; w.p = *p; w.ggamma0 = gr->gamma0; w.ggamma1 = gr->gamma1; w.wT0 = sv->wT0; w.wT1 = sv->wT1;
         w.gwT0 = ws + o_gw; w.gwL0 = w.gwT0 + GE * N; w.gwT1 = w.gwL0 + GE * N; w.gwL1 = w.gwT1 + GE * (N / 4);

@@ -15,6 +15,10 @@
 // Edge-weight gradients are NOT computed here: they only need the first-level stencils (s, h) and are a sum over a
 // graph's channels, which live in different CTAs here; block_gw.cu does them in one pass per stage.
 //
+// Planes wider than a 64-lane walker are cut into column strips of BW_STRIP valid columns with 8 halo columns per side
+// (the reach of one stage through the half-resolution branch); halo lanes compute throw-away values and are excluded
+// from every sum and store.
+//
 //   BW_X3 :  g = -a2 s1 gout                         z = x2   -> gx2
 //   BW_X2A:  g = -(b2 a2 s1 gout + a1 gx2)           z = x1   -> gx1 (A part)
 //   BW_X2B:  g =  (1+b2) a2 s1 gout + a1 gx2         z = x1   -> gx1 += (thresholded R part)
@@ -109,14 +113,17 @@ __device__ __forceinline__ Row w_core_thr_adj(const Row& hc, const Row& hu, cons
     return o;
 }
 
+#define BW_STRIP 240     // valid output columns of one strip of a plane wider than a 64-lane walker (8 halo columns per side)
 struct BwCta {
     int H, W, F, G, nch, b, g, f0, R0, R1, K0, K1, M, Wp;
+    int x0, v0, v1;      // first column of the walker's window; valid output columns [v0, v1)
     size_t HW;
 };
 __device__ __forceinline__ BwCta bw_cta(const StreamBwdArgs& a, int GL) {
     BwCta c;
     c.H = a.s.H; c.W = a.s.W; c.F = a.s.F; c.G = a.s.G; c.nch = a.nch;
     int bid = (int)blockIdx.x;
+    const int strip = bid % a.n_strips; bid /= a.n_strips;
     const int band = bid % a.n_bands; bid /= a.n_bands;
     const int chunks = c.F / c.nch;
     const int chunk = bid % chunks; bid /= chunks;
@@ -128,6 +135,13 @@ __device__ __forceinline__ BwCta bw_cta(const StreamBwdArgs& a, int GL) {
     c.M = (c.R1 - c.R0) + 7 + BW_DF;
     c.Wp = 4 * GL;
     c.HW = (size_t)c.H * c.W;
+    if (a.n_strips > 1) {
+        c.v0 = strip * BW_STRIP;
+        c.v1 = c.v0 + BW_STRIP < c.W ? c.v0 + BW_STRIP : c.W;
+        c.x0 = strip ? c.v0 - 8 : 0;
+    } else {
+        c.x0 = 0; c.v0 = 0; c.v1 = c.W;
+    }
     return c;
 }
 
@@ -185,7 +199,10 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
     const float Gam = THR ? expf(FINE ? a.p.gamma0[g] : a.p.gamma1[g]) : 0.f;
 
     LaneCtx lc;
-    lc.col0 = 4 * lane;
+    const int lcol = 4 * lane;                                  // column inside the walker's window (shared-memory rings)
+    lc.col0 = (FINE ? ct.x0 : ct.x0 / 2) + lcol;                // column in the plane of this resolution
+    // columns whose results count (a strip's halo lanes compute throw-away values)
+    const bool valid = FINE ? (lc.col0 >= ct.v0 && lc.col0 < ct.v1) : (lc.col0 >= ct.v0 / 2 && lc.col0 < ct.v1 / 2);
     lc.width = FINE ? (GL < 32 ? GL : 32) : (GL / 2 < 32 ? GL / 2 : 32);
     lc.active = live && lc.col0 < LW;
     lc.first = lc.col0 == 0;
@@ -200,7 +217,7 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
     const float* wsrc[BW_MAXJ];
     smem_addr_t wdst[BW_MAXJ];
     bool wlead[BW_MAXJ];
-    const float* wring0 = smem + (FINE ? lay.w0ring() : lay.w1ring()) + (size_t)PL0 * BW_WR * wpitch + lc.col0;   // my kind's plane 0, my quad
+    const float* wring0 = smem + (FINE ? lay.w0ring() : lay.w1ring()) + (size_t)PL0 * BW_WR * wpitch + lcol;   // my kind's plane 0, my quad
     {
         const float* base = ISL ? (FINE ? a.wL0 : a.wL1) + plane * 4 * LHW
                                 : THR ? (FINE ? a.wT0 : a.wT1) + plane * 4 * LHW : (FINE ? a.cT0 : a.cT1) + plane * 2 * LHW;
@@ -210,7 +227,7 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
             wsrc[j] = nullptr; wdst[j] = sbase; wlead[j] = false;
             if (lc.col0 < LW && e < NMY) {
                 wsrc[j] = base + (size_t)e * LHW + lc.col0;
-                wdst[j] = smem_advance(sbase, (int)(FINE ? lay.w0ring() : lay.w1ring()) + (PL0 + e) * BW_WR * wpitch + lc.col0);
+                wdst[j] = smem_advance(sbase, (int)(FINE ? lay.w0ring() : lay.w1ring()) + (PL0 + e) * BW_WR * wpitch + lcol);
                 wlead[j] = RAW && e == 0;
             }
         }
@@ -221,9 +238,9 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
         if (NOP > 1) opp[1] = a.op1 + off + lc.col0;
         if (NOP > 2 && has_skip) opp[2] = a.op2 + off + lc.col0;
     }
-    const smem_addr_t opdst = smem_advance(sbase, (int)lay.opring() + wkc * NOP * BW_OPR * Wp + lc.col0);
-    const smem_addr_t zdst = smem_advance(sbase, (int)lay.zring() + wkc * ZR * Wp + 2 * lc.col0);
-    const smem_addr_t s0dst = smem_advance(sbase, (int)lay.sring() + wkc * ZR * Wp + 2 * lc.col0);
+    const smem_addr_t opdst = smem_advance(sbase, (int)lay.opring() + wkc * NOP * BW_OPR * Wp + lcol);
+    const smem_addr_t zdst = smem_advance(sbase, (int)lay.zring() + wkc * ZR * Wp + 2 * lcol);
+    const smem_addr_t s0dst = smem_advance(sbase, (int)lay.sring() + wkc * ZR * Wp + 2 * lcol);
     const smem_addr_t s1dst = smem_advance(s0dst, nch * ZR * Wp);
     int zis = 0;
     const int r0 = FINE ? R0 : ct.K0;
@@ -300,7 +317,7 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
             // ---- rows t of z (clamp-extended at production) and of the upstream g (zero outside)
             if (t >= 0 && t < LH) {
                 if (FINE) {
-                    const int so = zs * Wp + lc.col0;
+                    const int so = zs * Wp + lcol;
                     z[N] = row_ld(zring + so);
                     const Row q0 = row_ld(s0ring + so);
                     Row q1 = row_zero();
@@ -308,7 +325,7 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
 #pragma unroll
                     for (int j = 0; j < 4; ++j) gq[N].v[j] = ca * q0.v[j] + cb * q1.v[j];
                 } else {
-                    const int so = zs * Wp + 2 * lc.col0;
+                    const int so = zs * Wp + 2 * lcol;
                     auto pool = [&](const float* ring, Row& dst) {
                         const float* p0 = ring + so;
                         const Row a0 = row_ld(p0), a1 = row_ld(p0 + 4), b0 = row_ld(p0 + Wp), b1 = row_ld(p0 + Wp + 4);
@@ -333,7 +350,7 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
             // scalars left / right of a z row that is still in the ring (fine) or in registers (coarse)
             auto z_lr = [&](const Row& zc, int back, float& l, float& r) {
                 if (FINE) {
-                    const float* p = zring + zslot(back) * Wp + lc.col0;
+                    const float* p = zring + zslot(back) * Wp + lcol;
                     l = lc.first ? zc.v[0] : p[-1];
                     r = lc.last ? zc.v[3] : p[4];
                 } else {
@@ -390,7 +407,7 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
                     }
                     float zl, zr;
                     z_lr(z[U], 2, zl, zr);           // z rows t-3 (z3), t-2 (z[U]), t-1 (z[C]); (shuffles: whole warp)
-                    if (lc.active && (FINE ? (r >= R0 && r < R1) : (r >= ct.K0 && r < ct.K1))) {
+                    if (lc.active && valid && (FINE ? (r >= R0 && r < R1) : (r >= ct.K0 && r < ct.K1))) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float gv = gs[N].v[j];
@@ -418,7 +435,7 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
                     float l, rr;
                     nb_lr<true, XWF>(o[C], l, rr, lc, BP_O);
                     Row fwd = w_St(kK, o[C], o[U], o[N], l, rr);
-                    const bool cnt = lc.active && (FINE || (r >= ct.K0 && r < ct.K1));
+                    const bool cnt = lc.active && valid && (FINE || (r >= ct.K0 && r < ct.K1));
                     if (cnt) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -445,11 +462,11 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
                     }
                     if (lc.active) {
                         if (FINE) {
-                            float* slot = xring + (((m & 1) * NK + KIND) * 2) * Wp + lc.col0;
+                            float* slot = xring + (((m & 1) * NK + KIND) * 2) * Wp + lcol;
                             st4(slot, V.v);
                             st4(slot + Wp, fwd.v);
                         } else {
-                            float* slot = cring + (((r & 3) * NK + KIND) * 2) * Wpc + lc.col0;
+                            float* slot = cring + (((r & 3) * NK + KIND) * 2) * Wpc + lcol;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) { V.v[j] *= 0.25f; fwd.v[j] *= 0.25f; }
                             st4(slot, V.v);
@@ -461,9 +478,9 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
             // ---- finisher: row t-4, everything its walkers posted one step ago
             if (FIN) {
                 const int r = t - 4;
-                if (r >= R0 && r < R1 && lc.active) {
-                    const float* xs = xring + (((m + 1) & 1) * NK * 2) * Wp + lc.col0;
-                    const float* cs = cring + (((r >> 1) & 3) * NK * 2) * Wpc + (lc.col0 >> 1);
+                if (r >= R0 && r < R1 && lc.active && valid) {
+                    const float* xs = xring + (((m + 1) & 1) * NK * 2) * Wp + lcol;
+                    const float* cs = cring + (((r >> 1) & 3) * NK * 2) * Wpc + (lcol >> 1);
                     Row V = row_ld(xs), Fw = row_ld(xs + Wp);
                     float2 cV = *reinterpret_cast<const float2*>(cs), cF = *reinterpret_cast<const float2*>(cs + Wpc);
                     if (HAS_L) {
@@ -473,11 +490,11 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
                         for (int j = 0; j < 4; ++j) { V.v[j] += VL.v[j]; Fw.v[j] += FL.v[j]; }
                         cV.x += cVL.x; cV.y += cVL.y; cF.x += cFL.x; cF.y += cFL.y;
                     }
-                    const int so = zslot(4) * Wp + lc.col0;
+                    const int so = zslot(4) * Wp + lcol;
                     const Row zq = row_ld(zring + so), q0 = row_ld(s0ring + so);
                     Row q1 = row_zero();
                     if (NSRC == 2) q1 = row_ld(s1ring + so);
-                    const float* ops = opring + (r & (BW_OPR - 1)) * Wp + lc.col0;
+                    const float* ops = opring + (r & (BW_OPR - 1)) * Wp + lcol;
                     Row p0 = row_zero(), p1 = row_zero(), p2 = row_zero(), outv;
                     if (NOP > 0) p0 = row_ld(ops);
                     if (NOP > 1) p1 = row_ld(ops + BW_OPR * Wp);
@@ -581,13 +598,14 @@ __global__ void __launch_bounds__(BwLaunch<MODE>::MAXT, BwLaunch<MODE>::MINB) k_
 // ---------------------------------------------------------------------------------------------------
 extern unsigned long long g_glr_stream_launches;
 struct BwPlan {
-    int GL, nch, threads, band_rows, n_bands;
+    int GL, nch, threads, band_rows, n_bands, n_strips;
 };
 template <int MODE>
 static BwPlan bw_plan(const glrgtv_shape& s) {
     constexpr bool HAS_L = BwSmem<MODE>::HAS_L;
     BwPlan p;
     p.GL = s.W > 128 ? 64 : s.W > 64 ? 32 : s.W > 32 ? 16 : 8;
+    p.n_strips = s.W > 256 ? (s.W + BW_STRIP - 1) / BW_STRIP : 1;
     auto threads = [&](int n) {
         const int nf = (n * p.GL + 31) & ~31, nc = (n * p.GL / 2 + 31) & ~31;
         return (HAS_L ? 2 : 1) * (nf + nc);
@@ -602,7 +620,7 @@ static BwPlan bw_plan(const glrgtv_shape& s) {
         p.nch = n;
     }
     p.threads = threads(p.nch);
-    const long ctas = (long)s.B * s.G * (s.F / p.nch);
+    const long ctas = (long)s.B * s.G * (s.F / p.nch) * p.n_strips;
     int bands = 1;
     while (ctas * bands < 296 && s.H / (bands * 2) >= 32) bands *= 2;
     p.band_rows = ((s.H + bands - 1) / bands + 1) & ~1;
@@ -627,8 +645,8 @@ template <int MODE>
 int glr_stream_bwd_stage(StreamBwdArgs a, int slot, void* stream) {
     const glrgtv_shape& s = a.s;
     const BwPlan p = bw_plan<MODE>(s);
-    a.nch = p.nch; a.band_rows = p.band_rows; a.n_bands = p.n_bands;
-    const long blocks = (long)s.B * s.G * (s.F / p.nch) * p.n_bands;
+    a.nch = p.nch; a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.n_strips = p.n_strips;
+    const long blocks = (long)s.B * s.G * (s.F / p.nch) * p.n_bands * p.n_strips;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
     GLR_PROF_BEGIN(slot, stream);
     const int rc = p.GL == 64 ? launch_bw_kernel<MODE, true>(a, p, blocks, stream) : launch_bw_kernel<MODE, false>(a, p, blocks, stream);

@@ -660,11 +660,7 @@ extern "C" int glrgtv_set_block_path(int mode) {
     return GLRGTV_OK;
 }
 
-// backward (and the TMA loader): a walker spans the whole row, at most two warps
-int glr_stream_eligible(const glrgtv_shape* s) {
-    return s->W % 8 == 0 && s->W <= 256 && s->H % 2 == 0 && s->H >= 2;
-}
-// forward: wider planes are cut into column strips of STREAM_STRIP valid columns (4K inference)
+// planes wider than a 64-lane walker are cut into column strips of STREAM_STRIP valid columns (4K inference, wide patches)
 int glr_stream_fwd_eligible(const glrgtv_shape* s) {
     return s->W % 8 == 0 && s->H % 2 == 0 && s->H >= 2;
 }

@@ -17,7 +17,7 @@ struct StreamBwdArgs {
     const float* op2;    // X3: x (skip)
     const float *wT0, *wL0, *wT1, *wL1, *cT0, *cT1;
     float* out;
-    int nch, band_rows, n_bands;
+    int nch, band_rows, n_bands, n_strips;
 };
 
 struct GwArgs {

@@ -203,8 +203,8 @@ typedef struct glrgtv_block_saved {
     float *cT0, *cT1;
 } glrgtv_block_saved;
 
-/* Which kernels the fused block entry points use: 0 = automatic (register-streaming kernels when W % 8 == 0 - the
- * backward additionally needs W <= 256 -, shared-memory plane kernels otherwise), 1 = plane kernels only, 2 = streaming kernels only
+/* Which kernels the fused block entry points use: 0 = automatic (register-streaming kernels when W % 8 == 0, planes
+ * wider than 256 in column strips; shared-memory plane kernels otherwise), 1 = plane kernels only, 2 = streaming kernels only
  * (GLRGTV_ERR_UNSUPPORTED for other shapes).  A debugging / test switch; both paths compute the same function. */
 int glrgtv_set_block_path(int mode);
 /* Loader of the streaming kernels: 0 = automatic (per stage, as measured), 1 = per-thread cp.async rings,

@@ -51,7 +51,7 @@ def test_stream_block_forward(case):
 
 
 @pytest.mark.parametrize("gw_streaming", [0, 1], ids=["gw_tiled", "gw_stream"])
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + [(3, 1, 1, 6, 272), (2, 1, 1, 4, 504)])
 def test_stream_block_backward(case, gw_streaming):
     dim, G, B, H, W = case
     E.emu_lib().glrgtv_set_gw_kernel(gw_streaming)

@@ -92,19 +92,31 @@ def test_streaming_equals_plane_kernels_at_benchmark_resolution(M, lib, case):
 
 
 def test_wide_planes(M, lib):
-    """W > 256: the forward streams in column strips (4K inference), the backward takes the plane kernels; both exact"""
+    """W > 256: forward and backward stream in column strips of 240 valid columns (4K inference, wide training patches)"""
     dim, G, B, H, W = 12, 2, 1, 24, 520
     sd = random_block_state(dim, G, seed=1)
     gen = torch.Generator().manual_seed(9)
     x, gout = torch.randn(B, dim, H, W, generator=gen), torch.randn(B, dim, H, W, generator=gen)
     ref = O.lowpass_block_fwd_bwd({k: v.double() for k, v in sd.items()}, x.double(), gout.double())
+    lib.glrgtv_set_block_path(2)
     n0 = lib.glrgtv_stream_launch_count()
     out, gx, pg = run_block(make_block(M, dim, G, sd), x, gout)
-    assert lib.glrgtv_stream_launch_count() - n0 == 4          # the four forward stages; no streaming backward kernels
+    assert lib.glrgtv_stream_launch_count() - n0 == 4 + 13
     check_against(out, gx, pg, *ref)
+
+
+def test_other_widths_take_the_plane_kernels(M, lib):
+    """W % 8 != 0 is outside the streaming kernels' range: automatic mode uses the plane kernels, forced mode raises"""
+    dim, G = 12, 2
+    blk = make_block(M, dim, G, random_block_state(dim, G, seed=1))
+    x = torch.randn(1, dim, 8, 268).cuda()
+    n0 = lib.glrgtv_stream_launch_count()
+    with torch.no_grad():
+        blk(x)
+    assert lib.glrgtv_stream_launch_count() == n0
     lib.glrgtv_set_block_path(2)
-    with pytest.raises(RuntimeError, match="UNSUPPORTED"):
-        run_block(make_block(M, dim, G, sd), x, gout)
+    with pytest.raises(RuntimeError, match="UNSUPPORTED"), torch.no_grad():
+        blk(x)
 
 
 def test_4k_row_forward(M, lib):
