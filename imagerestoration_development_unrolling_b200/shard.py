@@ -121,31 +121,51 @@ def exchange_row_halos_inplace(buf: torch.Tensor, top: int, bot: int, rank: int,
             buf[..., rows, :] = recv
 
 
+class CudaStageRunner:
+    """The pieces of one LocalLowpassFilteringBlock forward on a local plane, through glrgtv_block_fwd_stage.
+    (The CPU tests substitute a runner that drives the emulation build of the same kernels.)"""
+
+    def __init__(self, blk):
+        self.blk, self.lf = blk, blk.local_filter
+
+    def prepare(self, ext: torch.Tensor):
+        from . import ops
+        lf = self.lf
+        feat0, feat1 = lf._projections(ext)                   # per-pixel / 2x2-aligned: valid on the halo rows too
+        params = lf._block_params() + [self.blk.skip_weight]
+        saved = ops.alloc_block_saved(ext, lf.n_graphs)
+        st = dict(ext=ext, params=params, saved=saved, names=dict(zip(ops._SAVED, saved)), out=torch.empty_like(ext))
+        ops.lowpass_block_stage(0, ext, feat0.contiguous(), feat1.contiguous(), params, lf.n_graphs, saved, st["out"], 0, ext.shape[-2])
+        return st
+
+    def stage(self, st, k: int, row0: int, row1: int) -> None:
+        from . import ops
+        ops.lowpass_block_stage(k, st["ext"], None, None, st["params"], self.lf.n_graphs, st["saved"], st["out"], row0, row1)
+
+    def buffer(self, st, name: str) -> torch.Tensor:
+        return st["names"][name].view(st["ext"].shape)        # [B,G,F,H,W] -> [B,C,H,W]
+
+    def output(self, st) -> torch.Tensor:
+        return st["out"]
+
+
 @torch.no_grad()
-def sharded_block_forward_staged(blk, strip: torch.Tensor, rank: int, world: int, group=None) -> torch.Tensor:
+def sharded_block_forward_staged(blk, strip: torch.Tensor, rank: int, world: int, group=None, runner=None) -> torch.Tensor:
     """LocalLowpassFilteringBlock on this rank's row strip with ONE 8-row halo exchange PER SOLVER STAGE instead of one
     26-row exchange per block: x, bA, x1 and x2 are exchanged, every stage computes exactly the rank's own rows
     (glrgtv_block_fwd_stage), so nothing but the edge weights of the 8 halo rows is computed twice.  Exact: a stage reaches
     at most 7 rows beyond the rows it produces.  `blk` is the drop-in module (its streaming kernels: W % 8 == 0)."""
-    from . import ops
-    if world == 1:
+    if world == 1 and runner is None:
         return blk(strip)
     if strip.shape[-2] < 2 * STAGE_HALO_ROWS:
         raise ValueError(f"strip of {strip.shape[-2]} rows is too thin for two {STAGE_HALO_ROWS}-row halos")
+    runner = runner or CudaStageRunner(blk)
     ext, t, b = exchange_row_halos(strip, STAGE_HALO_ROWS, rank, world, group)
-    ext = ext.contiguous()
-    lf = blk.local_filter
-    feat0, feat1 = lf._projections(ext)                   # per-pixel / 2x2-aligned: valid on the halo rows too
-    params = lf._block_params() + [blk.skip_weight]
-    saved = ops.alloc_block_saved(ext, lf.n_graphs)
-    names = dict(zip(ops._SAVED, saved))
-    out = torch.empty_like(ext)
+    st = runner.prepare(ext.contiguous())
     H = ext.shape[-2]
     r0, r1 = t, H - b
-    ops.lowpass_block_stage(0, ext, feat0.contiguous(), feat1.contiguous(), params, lf.n_graphs, saved, out, 0, H)
-    for stage, produced in ((1, "bA"), (2, "x1"), (3, "x2")):
-        ops.lowpass_block_stage(stage, ext, None, None, params, lf.n_graphs, saved, out, r0, r1)
-        buf = names[produced].view(ext.shape)             # [B,G,F,H,W] -> [B,C,H,W]
-        exchange_row_halos_inplace(buf, t, b, rank, world, group)
-    ops.lowpass_block_stage(4, ext, None, None, params, lf.n_graphs, saved, out, r0, r1)
-    return out[..., r0:r1, :].contiguous()
+    for k, produced in ((1, "bA"), (2, "x1"), (3, "x2")):
+        runner.stage(st, k, r0, r1)
+        exchange_row_halos_inplace(runner.buffer(st, produced), t, b, rank, world, group)
+    runner.stage(st, 4, r0, r1)
+    return runner.output(st)[..., r0:r1, :].contiguous()

@@ -200,3 +200,16 @@ def test_staged_strips_equal_the_whole_plane(M, lib, world):
         got = torch.cat([s["out"][..., s["t"]:s["out"].shape[-2] - s["b"], :] for s in st], dim=-2)
     assert torch.isfinite(got).all()
     assert rel(got, full) < 1e-6, rel(got, full)
+
+
+def test_cuda_stage_runner_single_rank(M, lib):
+    """shard.sharded_block_forward_staged through its CUDA runner with world = 1 (no neighbours): weights + four stages
+    on the whole plane equal the one-call forward"""
+    from imagerestoration_development_unrolling_b200 import shard
+    dim, G = 48, 8
+    blk = make_block(M, dim, G, random_block_state(dim, G, seed=3))
+    x = torch.randn(1, dim, 40, 264, generator=torch.Generator().manual_seed(2)).cuda()
+    with torch.no_grad():
+        ref = blk(x)
+        got = shard.sharded_block_forward_staged(blk, x, 0, 1, runner=shard.CudaStageRunner(blk))
+    assert rel(got, ref) < 1e-6
