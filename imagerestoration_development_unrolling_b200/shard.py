@@ -169,3 +169,94 @@ def sharded_block_forward_staged(blk, strip: torch.Tensor, rank: int, world: int
         exchange_row_halos_inplace(runner.buffer(st, produced), t, b, rank, world, group)
     runner.stage(st, 4, r0, r1)
     return runner.output(st)[..., r0:r1, :].contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- whole-model inference
+def conv3x3_on_strip(conv: torch.nn.Conv2d, strip: torch.Tensor, rank: int, world: int, group=None) -> torch.Tensor:
+    """A replicate-padded 3x3 convolution (the host CNN's only spatial operator besides the aligned 2x2 re-sampling,
+    V1X0:929-948, 992-1005) on a row strip: one row from each neighbour inside the image, replicate padding at the true
+    image border and at the left / right edges - the rows the whole-image convolution would have seen."""
+    if conv.kernel_size != (3, 3) or conv.stride != (1, 1) or conv.dilation != (1, 1) or conv.padding_mode != "replicate":
+        raise ValueError("conv3x3_on_strip expects the host CNN's 3x3 / stride 1 / replicate-padded convolution")
+    ext, t, b = exchange_row_halos(strip, 1, rank, world, group)
+    ext = torch.nn.functional.pad(ext, (1, 1, 1 - t, 1 - b), mode="replicate")
+    return torch.nn.functional.conv2d(ext, conv.weight, conv.bias, 1, 0, 1, conv.groups)
+
+
+class ShardedMultiScaleFilter:
+    """AbtractMultiScaleGraphFilter (V1X0:1028-1173) on ONE rank's row strip of a spatially sharded image: the same
+    `encode / filtering / decode / enc_dec / forward` surface, every tensor a [B,C,rows,W] strip.
+
+    What crosses ranks: one row per 3x3 convolution (45 of them in the shipped v13 model: the embedding and one depthwise
+    convolution in each of the 44 LocalNonLinearBlocks) and the filter blocks' per-stage halos
+    (`sharded_block_forward_staged`).  Everything else in the host CNN is per pixel (variance norm, 1x1 convolutions, gate,
+    skips, channel concat) or an aligned 2x2 stride-2 down / up-sampling, which never straddles a strip boundary because
+    strips start at multiples of 16 input rows (`strip_bounds(H, world, align=16)`).
+
+    `block_forward(blk, strip, scale)` runs one LocalLowpassFilteringBlock on a strip; the default is the staged exchange
+    over the module's CUDA kernels (the CPU tests plug the emulation build in here)."""
+
+    ALIGN = 16
+
+    def __init__(self, model, rank: int, world: int, group=None, block_forward=None):
+        self.model, self.rank, self.world, self.group = model, rank, world, group
+        self.block_forward = block_forward or (lambda blk, strip, scale: sharded_block_forward_staged(blk, strip, rank, world, group))
+
+    # -- pieces of the host CNN
+    def nonlinear_block(self, blk, x: torch.Tensor) -> torch.Tensor:
+        """LocalNonLinearBlock (V1X0:951-964) on a strip; only its depthwise 3x3 needs neighbour rows."""
+        ll = blk.local_linear
+        h = ll.channels_linear_op(blk.norm(x))
+        gate, val = conv3x3_on_strip(ll.channels_local_linear_op, h, self.rank, self.world, self.group).chunk(2, dim=1)
+        return blk.skip_weight[0] * x + blk.skip_weight[1] * ll.project_out(torch.sigmoid(gate) * gate * val)
+
+    def stack(self, blocks, x: torch.Tensor) -> torch.Tensor:
+        for blk in blocks:
+            x = self.nonlinear_block(blk, x)
+        return x
+
+    def _check(self, img: torch.Tensor) -> None:
+        if img.shape[-2] % self.ALIGN or img.shape[-1] % self.ALIGN:
+            raise ValueError(f"strip of {img.shape[-2]}x{img.shape[-1]}: rows and width must be multiples of {self.ALIGN} "
+                             "(pad the image first, evalpipe.pad_to_factor; cut strips with strip_bounds(H, world, align=16))")
+
+    # -- the reference's surface
+    def encode(self, img: torch.Tensor):
+        self._check(img)
+        m = self.model
+        x = conv3x3_on_strip(m.patch_3x3_embeding.channels_local_linear_op01, img, self.rank, self.world, self.group)
+        x = self.stack(m.encoder_scale_00, x)
+        outs = [x]
+        for i in (1, 2, 3):
+            x = self.stack(getattr(m, f"encoder_scale_0{i}"), getattr(m, f"down_sample_0{i - 1}_0{i}")(x))
+            outs.append(x)
+        return tuple(outs)
+
+    def filtering(self, coefs):
+        return tuple(self.block_forward(getattr(self.model, f"localfilter_scale_0{i}"), c.contiguous(), i) for i, c in enumerate(coefs))
+
+    def decode(self, coefs):
+        m = self.model
+        x = coefs[3]
+        for i in (2, 1, 0):
+            up = getattr(m, f"up_sample_0{i + 1}_0{i}")(x)
+            x = getattr(m, f"combine_channels_0{i}")(torch.cat([up, coefs[i]], 1))
+            x = self.stack(getattr(m, f"decoder_scale_0{i}"), x)
+        return m.linear_output(self.stack(m.refining_block, x))
+
+    def enc_dec(self, img: torch.Tensor) -> torch.Tensor:
+        return self.decode(self.encode(img))
+
+    @torch.no_grad()
+    def forward(self, img: torch.Tensor) -> torch.Tensor:
+        return self.decode(self.filtering(self.encode(img)))
+
+    __call__ = forward
+
+
+@torch.no_grad()
+def sharded_restore(model, image: torch.Tensor, rank: int, world: int, group=None, block_forward=None) -> torch.Tensor:
+    """Config 4 end to end: every rank holds the whole padded [B,3,H,W] input (H, W multiples of 16), restores its own row
+    strip with ShardedMultiScaleFilter and returns that strip ([B,3,rows,W]); `strip_bounds(H, world, 16)[rank]` says which rows."""
+    a, b = strip_bounds(image.shape[-2], world, ShardedMultiScaleFilter.ALIGN)[rank]
+    return ShardedMultiScaleFilter(model, rank, world, group, block_forward)(image[..., a:b, :].contiguous())

@@ -3,7 +3,8 @@
     torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
 
 (1) spatially sharded inference of a filter block (row strips + NCCL halo exchange) equals the single-GPU result;
-(2) batch-sharded training: all-reduced parameter gradients equal the gradients of the concatenated batch."""
+(2) batch-sharded training: all-reduced parameter gradients equal the gradients of the concatenated batch;
+(3) the whole v13 network on row strips (shard.ShardedMultiScaleFilter) equals the network on the whole image."""
 import os
 import sys
 
@@ -69,6 +70,26 @@ def main():
     if rank == 0:
         print(f"batch-sharded training, {world} ranks: worst relative gradient error vs the full batch = {float(t):.2e}")
     assert float(t) < 1e-4
+
+    # (3) whole network, spatially sharded: 128 input rows per rank (16 rows at 1/8 resolution: the thinnest strip the
+    #     per-stage exchange takes), width 256
+    torch.manual_seed(2)
+    net = M.AbtractMultiScaleGraphFilter(dims=[48, 96, 192, 384], hidden_dims=[96, 192, 384, 768], nsubnets=[1, 1, 1, 1],
+                                         ngraphs=[8, 16, 16, 32], num_blocks=[4, 6, 6, 8], num_blocks_out=4).to(dev).eval()
+    for i in range(4):
+        fb = getattr(net, f"localfilter_scale_0{i}")
+        fb.load_state_dict(randomize_block_state({k: v.cpu().clone() for k, v in fb.state_dict().items()}, seed=30 + i))
+    img = torch.rand(1, 3, 128 * world, 256, generator=gen).to(dev)
+    a, b = shard.strip_bounds(img.shape[-2], world, align=16)[rank]
+    with torch.no_grad():
+        full = net(img)
+        mine = shard.sharded_restore(net, img, rank, world)
+    err = float((mine - full[:, :, a:b]).abs().max() / full.abs().max())
+    t = torch.tensor([err], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"whole v13 network on {world} row strips of a {img.shape[-2]}x256 image: max rel err vs single GPU = {float(t):.2e}")
+    assert float(t) < 1e-5
     dist.destroy_process_group()
 
 

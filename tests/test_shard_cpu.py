@@ -196,3 +196,87 @@ def test_staged_sharded_block_equals_full_image(world):
     got = torch.cat([torch.from_numpy(res[r]) for r in range(world)], dim=2)
     assert got.shape == full.shape and torch.isfinite(got).all()
     assert float((got.double() - full).norm() / full.norm()) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------- whole model on strips
+def _tiny_model(seed=3):
+    from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
+    torch.manual_seed(seed)
+    m = M.AbtractMultiScaleGraphFilter(dims=[8, 8, 12, 8], hidden_dims=[8, 12, 8, 8], ngraphs=[2, 2, 2, 2],
+                                       num_blocks=[2, 1, 1, 1], num_blocks_out=1).eval()
+    with torch.no_grad():          # move the filter blocks and the skips off their init, as every parity test does
+        for i in range(4):
+            blk = getattr(m, f"localfilter_scale_0{i}")
+            blk.load_state_dict(O.randomize_block_state({k: v.clone() for k, v in blk.state_dict().items()}, 20 + i))
+        for n, p in m.named_parameters():
+            if n.endswith("skip_weight") and "localfilter" not in n:
+                p.copy_(torch.tensor([0.8, 0.6]))
+    return m
+
+
+def _oracle_filtering(m, coefs):
+    outs = []
+    for i, c in enumerate(coefs):
+        sd = {k: v.double() for k, v in getattr(m, f"localfilter_scale_0{i}").state_dict().items()}
+        outs.append(O.lowpass_block_forward(sd, c.double()).float())
+    return tuple(outs)
+
+
+def _model_worker(rank, world, port, q, img, with_blocks):
+    _init(rank, world, port)
+    m = _tiny_model()
+
+    def emu_block(blk, strip, scale):
+        sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+        return shard.sharded_block_forward_staged(None, strip, rank, world, runner=EmuStageRunner(sd, blk.local_filter.n_graphs))
+
+    ex = shard.ShardedMultiScaleFilter(m, rank, world, block_forward=emu_block)
+    a, b = shard.strip_bounds(img.shape[-2], world, ex.ALIGN)[rank]
+    strip = img[:, :, a:b].contiguous()
+    with torch.no_grad():
+        out = ex(strip) if with_blocks else ex.enc_dec(strip)
+    q.put((rank, out.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_model(world, img, with_blocks):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_model_worker, args=(r, world, port, q, img, with_blocks)) for r in range(world)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=600) for _ in range(world))
+    [p.join(60) for p in procs]
+    return torch.cat([torch.from_numpy(res[r]) for r in range(world)], dim=2)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_host_cnn_equals_full_image(world):
+    """encoder + decoder of the 4-scale model on row strips (one exchanged row per 3x3 convolution, aligned 2x2 re-sampling)
+    against the module on the whole image; strips of unequal height (world 3: 32 + 32 + 16 rows)"""
+    img = torch.rand(2, 3, 80 if world == 3 else 64, 32, generator=torch.Generator().manual_seed(8))
+    m = _tiny_model()
+    with torch.no_grad():
+        full = m.enc_dec(img)
+    got = _run_model(world, img, with_blocks=False)
+    assert got.shape == full.shape
+    assert float((got - full).abs().max()) < 1e-5 * float(full.abs().max())
+
+
+def test_sharded_whole_model_equals_full_image():
+    """config 4 in miniature: the whole AbtractMultiScaleGraphFilter on two row strips - host CNN with row exchanges, the four
+    filter blocks through the per-stage halo exchange on the emulated CUDA kernels - against the module's CNN + the oracle blocks"""
+    img = torch.rand(1, 3, 256, 64, generator=torch.Generator().manual_seed(9))
+    m = _tiny_model()
+    with torch.no_grad():
+        full = m.decode(_oracle_filtering(m, m.encode(img)))
+    got = _run_model(2, img, with_blocks=True)
+    assert got.shape == full.shape and torch.isfinite(got).all()
+    assert float((got - full).norm() / full.norm()) < 1e-5
+
+
+def test_sharded_model_rejects_unaligned_strips():
+    m = _tiny_model()
+    with pytest.raises(ValueError, match="multiples of 16"):
+        shard.ShardedMultiScaleFilter(m, 0, 1).encode(torch.rand(1, 3, 40, 32))

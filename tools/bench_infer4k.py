@@ -6,6 +6,9 @@
 The four LocalLowpassFilteringBlock of the v13 model run (no_grad) on the feature maps of one 3840x2160 image:
 [1,48,2160,3840], [1,96,1080,1920], [1,192,540,960], [1,384,270,480].  With N ranks every map is cut into N row
 strips (boundaries at even rows) and each block does one 26-row NCCL halo exchange (shard.sharded_block_forward).
+`--staged`: one 8-row exchange per solver stage instead.  `--model`: the WHOLE v13 network (host CNN on strips with one
+exchanged row per 3x3 convolution + the staged filter blocks, shard.ShardedMultiScaleFilter) on the 3-channel image.
+`--steps K --warmup W` (default 5 / 3).
 Prints one JSON line: Mpix/s of the network input (8.29 Mpix per image), max over ranks of the CUDA-event time."""
 import json
 import os
@@ -33,26 +36,40 @@ def main():
     torch.manual_seed(0)
     blocks = [M.LocalLowpassFilteringBlock(d, 1, g).to(dev) for d, g in zip(DIMS, NG)]
     strips = []
-    for s, d in enumerate(DIMS):
+    for s, d in enumerate(DIMS if "--model" not in sys.argv else []):
         H, W = H0 >> s, W0 >> s
         a, b = shard.strip_bounds(H, world, align=2)[rank]
         strips.append(torch.randn(1, d, b - a, W, device=dev, generator=torch.Generator(device=dev).manual_seed(s)))
 
     staged = "--staged" in sys.argv       # one 8-row exchange per solver stage instead of one 26-row exchange per block
+    whole = "--model" in sys.argv
+
+    def flag(name, default):
+        return int(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
+
+    steps, warmup = flag("--steps", 5), flag("--warmup", 3)
+    if whole:
+        torch.manual_seed(0)
+        net = M.AbtractMultiScaleGraphFilter(dims=DIMS, hidden_dims=[96, 192, 384, 768], nsubnets=[1, 1, 1, 1], ngraphs=NG,
+                                             num_blocks=[4, 6, 6, 8], num_blocks_out=4).to(dev).eval()
+        a, b = shard.strip_bounds(H0, world, align=16)[rank]
+        img = torch.rand(1, 3, b - a, W0, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        ex = shard.ShardedMultiScaleFilter(net, rank, world)
 
     def run():
         with torch.no_grad():
+            if whole:
+                return ex(img)
             if staged:
                 return [shard.sharded_block_forward_staged(blk, x, rank, world) for blk, x in zip(blocks, strips)]
             return [shard.sharded_block_forward(blk, x, rank, world) for blk, x in zip(blocks, strips)]
 
-    for _ in range(3):
+    for _ in range(warmup):
         run()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    steps = 5
     e0.record()
     for _ in range(steps):
         run()
@@ -66,8 +83,11 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "infer_Mpix_per_s", "value": H0 * W0 / ms / 1e3, "unit": "Mpix/s", "n_gpus": world,
                           "ms_per_image": ms, "scaling": "strong", "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "v13 four filter blocks, forward, feature maps of one 3840x2160 image, row strips, "
-                                                 + ("8-row halo exchange per solver stage" if staged else "26-row halo exchange per block")}}))
+                          "steps": steps, "warmup": warmup,
+                          "config": {"workload": ("whole v13 network, one 3840x2160 image, row strips, one row per 3x3 convolution + 8-row halo "
+                                                  "exchange per solver stage") if whole else
+                                     "v13 four filter blocks, forward, feature maps of one 3840x2160 image, row strips, "
+                                     + ("8-row halo exchange per solver stage" if staged else "26-row halo exchange per block")}}))
     if world > 1:
         dist.destroy_process_group()
 
