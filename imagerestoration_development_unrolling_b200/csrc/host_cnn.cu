@@ -1,0 +1,176 @@
+// host_cnn.cu - the HBM-bound part of LocalNonLinearBlock (V1X0:911-964), inference forward (first cut).
+//
+//   reference:  n = CustomLayerNorm(x) = w_n * x / sqrt(var_c(x) + 1e-5)            (V1X0:911-925, per pixel, per sub-net)
+//               h = conv1x1(n)  [2 Hd channels]                                      (V1X0:933-937)
+//               m = depthwise 3x3 (replicate padded) of h; gate, val = m.chunk(2)    (V1X0:938-946)
+//               out = s0 x + s1 conv1x1(sigmoid(gate) gate val)                      (V1X0:947, 961-964)
+//
+// The per-pixel scale rs = 1/sqrt(var + eps) commutes with the 1x1 convolution, so the normalised tensor is never written:
+//   k_pixel_rstd :  x -> rs [B, nsub, H, W]                                  reads x once (4 C bytes per pixel)
+//   (GEMM, cuBLAS):  h_raw = (W1 diag(w_n)) x
+//   k_dwconv_gate:  h_raw, rs -> u = sigmoid(G) G V,  G | V = dw3x3(rs h_raw)   reads h once, writes u (12 Hd bytes per pixel)
+//   (GEMM, cuBLAS):  out = s0 x + (s1 W2) u
+// instead of the reference's eleven passes (variance, divide, scale, pad, conv, chunk copies, sigmoid, two products, skip).
+// On a row strip of a spatially sharded image the rows above / below come from the neighbours as already scaled rows
+// (`top` / `bot`, [B, 2Hd, W]); NULL means the true image border (replicate).
+#include "tile.cuh"
+
+// one item = 4 consecutive pixels of one (image, sub-net): Welford over the sub-net's channels (the reference's
+// torch.var is two-pass; a sum / sum-of-squares form would cancel for features with a large mean)
+__global__ void __launch_bounds__(256) k_pixel_rstd(const float* __restrict__ x, float* __restrict__ rs, int B, int nsub, int c,
+                                                    long HW, float eps) {
+    const long Q = HW / 4, total = (long)B * nsub * Q;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long q = i % Q, bs = i / Q;
+        const float* p = x + bs * c * HW + 4 * q;
+        float mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < c; ++k) {
+            float v[4];
+            ld4(p + (long)k * HW, v);
+            const float inv = 1.f / (float)(k + 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = v[j] - mean[j];
+                mean[j] += d * inv;
+                m2[j] += d * (v[j] - mean[j]);
+            }
+        }
+        const float invn = 1.f / (float)(c - 1);
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = 1.f / sqrtf(m2[j] * invn + eps);
+        st4(rs + bs * HW + 4 * q, o);
+    }
+}
+
+// a scaled row segment: the thread's 4 columns and the scalars left / right of them
+struct SegRow {
+    float l, v[4], r;
+};
+#define DW_BAND 32      // rows one thread walks (2 halo rows re-read per band: 6 %)
+
+struct DwArgs {
+    const float *h, *rs, *w9, *top, *bot;
+    float* u;
+    int B, Hd, nsub, H, W, n_bands;
+};
+
+// raw operands of one row of a gate / value channel pair: the thread's quads of h and of rs, and - on the lanes at a warp's
+// edge only - the already scaled scalars left / right of the quad (the other lanes get them from their neighbours' registers)
+struct RawRow {
+    float g[4], v[4], sg[4], sv[4], gl, gr, vl, vr;
+};
+template <bool ONE>      // ONE: a single sub-net, gate and value share rs
+__device__ __forceinline__ RawRow dw_load(const DwArgs& a, int b, int k, int row, int q, bool need_l, bool need_r) {
+    RawRow o;
+    const int cg = k, cv = a.Hd + k;
+    if ((row < 0 && a.top) || (row >= a.H && a.bot)) {           // the neighbour strip's row: already scaled
+        const float* base = (row < 0 ? a.top : a.bot) + (long)b * 2 * a.Hd * a.W + 4 * q;
+        const float *pg = base + (long)cg * a.W, *pv = base + (long)cv * a.W;
+        ld4(pg, o.g); ld4(pv, o.v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.sg[j] = o.sv[j] = 1.f;
+        o.gl = need_l ? pg[-1] : 0.f; o.vl = need_l ? pv[-1] : 0.f;
+        o.gr = need_r ? pg[4] : 0.f; o.vr = need_r ? pv[4] : 0.f;
+        return o;
+    }
+    row = row < 0 ? 0 : row >= a.H ? a.H - 1 : row;              // the true image border replicates
+    const float* pg = a.h + (((long)b * 2 * a.Hd + cg) * a.H + row) * a.W + 4 * q;
+    const float* pv = a.h + (((long)b * 2 * a.Hd + cv) * a.H + row) * a.W + 4 * q;
+    const int per = 2 * a.Hd / a.nsub;
+    const float* rg = a.rs + (((long)b * a.nsub + (ONE ? 0 : cg / per)) * a.H + row) * a.W + 4 * q;
+    const float* rv = ONE ? rg : a.rs + (((long)b * a.nsub + cv / per) * a.H + row) * a.W + 4 * q;
+    ld4(pg, o.g); ld4(pv, o.v); ld4(rg, o.sg);
+    if (!ONE) ld4(rv, o.sv);
+    o.gl = need_l ? pg[-1] * rg[-1] : 0.f; o.vl = need_l ? pv[-1] * rv[-1] : 0.f;
+    o.gr = need_r ? pg[4] * rg[4] : 0.f; o.vr = need_r ? pv[4] * rv[4] : 0.f;
+    return o;
+}
+// scale, and fetch the scalars beside the quad from the neighbouring lanes (whole warp calls this)
+template <bool ONE>
+__device__ __forceinline__ void dw_finish(const RawRow& w, bool first, bool last, bool need_l, bool need_r, SegRow& G, SegRow& V) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { G.v[j] = w.g[j] * w.sg[j]; V.v[j] = w.v[j] * (ONE ? w.sg[j] : w.sv[j]); }
+    const float gl = __shfl_up_sync(0xffffffffu, G.v[3], 1), gr = __shfl_down_sync(0xffffffffu, G.v[0], 1);
+    const float vl = __shfl_up_sync(0xffffffffu, V.v[3], 1), vr = __shfl_down_sync(0xffffffffu, V.v[0], 1);
+    G.l = first ? G.v[0] : need_l ? w.gl : gl; G.r = last ? G.v[3] : need_r ? w.gr : gr;
+    V.l = first ? V.v[0] : need_l ? w.vl : vl; V.r = last ? V.v[3] : need_r ? w.vr : vr;
+}
+__device__ __forceinline__ void dw_acc(const float (&w)[9], int dy, const SegRow& s, float (&o)[4]) {
+    const float e[6] = {s.l, s.v[0], s.v[1], s.v[2], s.v[3], s.r};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] += w[3 * dy] * e[j] + w[3 * dy + 1] * e[j + 1] + w[3 * dy + 2] * e[j + 2];
+}
+
+// one item = 4 columns x DW_BAND rows of one gate / value channel pair; consecutive threads = consecutive column quads (the
+// lanes of a warp exchange the scalars at their quads' edges), then channel pairs (so that the CTAs in flight share the same
+// rows of rs in L2), then bands, then images.  The operands of row r+2 are loaded while row r is computed.
+template <bool ONE>
+__global__ void __launch_bounds__(128) k_dwconv_gate(DwArgs a) {
+    const int Q = a.W / 4, lane = (int)(threadIdx.x & 31u);
+    const long total = (long)a.B * a.n_bands * a.Hd * Q, padded = (total + 31) & ~31L;       // whole warps iterate together
+    for (long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x; i0 < padded; i0 += (long)gridDim.x * blockDim.x) {
+        const bool act = i0 < total;
+        const long i = act ? i0 : total - 1;
+        const int q = (int)(i % Q), k = (int)((i / Q) % a.Hd);
+        const int band = (int)((i / ((long)Q * a.Hd)) % a.n_bands), b = (int)(i / ((long)Q * a.Hd * a.n_bands));
+        const int r0 = band * DW_BAND, r1 = r0 + DW_BAND < a.H ? r0 + DW_BAND : a.H;
+        const bool first = q == 0, last = q == Q - 1;
+        const bool need_l = lane == 0 && !first, need_r = lane == 31 && !last;
+        float wg[9], wv[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) { wg[t] = a.w9[k * 9 + t]; wv[t] = a.w9[(a.Hd + k) * 9 + t]; }
+        SegRow gU, gC, gD, vU, vC, vD;
+        {
+            const RawRow wU = dw_load<ONE>(a, b, k, r0 - 1, q, need_l, need_r), wC = dw_load<ONE>(a, b, k, r0, q, need_l, need_r);
+            dw_finish<ONE>(wU, first, last, need_l, need_r, gU, vU);
+            dw_finish<ONE>(wC, first, last, need_l, need_r, gC, vC);
+        }
+        RawRow nxt = dw_load<ONE>(a, b, k, r0 + 1, q, need_l, need_r);
+        float* dst = a.u + (((long)b * a.Hd + k) * a.H + r0) * a.W + 4 * q;
+        // every lane of a warp walks the same number of rows (its lanes may sit in different bands: the shuffles need them all)
+        const int rend = r0 + (a.H < DW_BAND ? a.H : DW_BAND);
+        for (int r = r0; r < rend; ++r, dst += a.W) {
+            const RawRow nxt2 = dw_load<ONE>(a, b, k, r + 2, q, need_l, need_r);              // rows past H clamp: harmless re-reads
+            dw_finish<ONE>(nxt, first, last, need_l, need_r, gD, vD);
+            float G[4] = {0.f, 0.f, 0.f, 0.f}, V[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+            dw_acc(wg, 0, gU, G); dw_acc(wg, 1, gC, G); dw_acc(wg, 2, gD, G);
+            dw_acc(wv, 0, vU, V); dw_acc(wv, 1, vC, V); dw_acc(wv, 2, vD, V);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = G[j] / (1.f + expf(-G[j])) * V[j];
+            if (act && r < r1) st4(dst, o);
+            gU = gC; gC = gD; vU = vC; vC = vD;
+            nxt = nxt2;
+        }
+    }
+}
+
+static inline bool misaligned16(const void* p) { return ((uintptr_t)p & 15u) != 0; }
+
+// x [B, C, H*W] -> rs [B, nsub, H*W] = 1 / sqrt(unbiased variance over each sub-net's C / nsub channels + eps).  HW % 4 == 0.
+extern "C" int glrgtv_pixel_rstd(int B, int C, int nsub, long HW, float eps, const float* x, float* rs, void* stream) {
+    if (B <= 0 || C <= 0 || nsub <= 0 || HW <= 0 || C % nsub || C / nsub < 2) return GLRGTV_ERR_SHAPE;
+    if (HW % 4) return GLRGTV_ERR_UNSUPPORTED;
+    if (!x || !rs || misaligned16(x) || misaligned16(rs)) return GLRGTV_ERR_POINTER;
+    const long total = (long)B * nsub * (HW / 4), blocks = (total + 255) / 256;
+    GLR_LAUNCH_FIBERS(k_pixel_rstd, dim3((unsigned)(blocks > 148 * 64 ? 148 * 64 : blocks)), 256, 0, stream, x, rs, B, nsub, C / nsub, HW, eps);
+    return GLR_CHECK_LAUNCH();
+}
+
+// h [B, 2Hd, H, W] (un-normalised 1x1 output), rs [B, nsub, H, W], w9 [2Hd, 9] (the depthwise 3x3 weights), top / bot
+// [B, 2Hd, W] already scaled neighbour rows or NULL (replicate) -> u [B, Hd, H, W].  W % 4 == 0, (2 Hd) % nsub == 0.
+extern "C" int glrgtv_dwconv_gate(int B, int Hd, int nsub, int H, int W, const float* h, const float* rs, const float* w9,
+                                  const float* top, const float* bot, float* u, void* stream) {
+    if (B <= 0 || Hd <= 0 || nsub <= 0 || H <= 0 || W <= 0 || (2 * Hd) % nsub) return GLRGTV_ERR_SHAPE;
+    if (W % 4) return GLRGTV_ERR_UNSUPPORTED;
+    if (!h || !rs || !w9 || !u || misaligned16(h) || misaligned16(rs) || misaligned16(u) || (top && misaligned16(top)) || (bot && misaligned16(bot)))
+        return GLRGTV_ERR_POINTER;
+    DwArgs a;
+    a.h = h; a.rs = rs; a.w9 = w9; a.top = top; a.bot = bot; a.u = u;
+    a.B = B; a.Hd = Hd; a.nsub = nsub; a.H = H; a.W = W; a.n_bands = (H + DW_BAND - 1) / DW_BAND;
+    const long total = (long)B * a.n_bands * Hd * (W / 4), blocks = (total + 127) / 128;
+    if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;
+    if (nsub == 1) GLR_LAUNCH_FIBERS(k_dwconv_gate<true>, dim3((unsigned)blocks), 128, 0, stream, a);
+    else GLR_LAUNCH_FIBERS(k_dwconv_gate<false>, dim3((unsigned)blocks), 128, 0, stream, a);
+    return GLR_CHECK_LAUNCH();
+}

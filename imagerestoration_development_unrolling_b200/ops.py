@@ -15,7 +15,7 @@ Operator <-> reference method (V1X0 = deep_multiscale_GGLR_GGTV_v1x0.py):
   pool2 / unpool2   the 0.25 depthwise 2x2 (transposed) conv  V1X0:613, 662-679
   lowpass_block     LocalLowpassFilteringBlock.forward     V1X0:707-811, 985-988
 """
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -428,6 +428,31 @@ def _pg_backward(ctx, gy):
 
 
 proj_gemm.register_autograd(_pg_backward, setup_context=_pg_setup)
+
+
+# ---- host CNN, inference forward: the memory-bound pieces of LocalNonLinearBlock (host_cnn.py)
+def pixel_rstd(x: Tensor, nsub: int, eps: float) -> Tensor:
+    """x [B,C,H,W] -> [B,nsub,H,W]: 1 / sqrt(unbiased variance over each sub-net's channels + eps); glrgtv_pixel_rstd"""
+    _chk(x)
+    x = _c(x)
+    B, C, H, W = x.shape
+    rs = x.new_empty(B, nsub, H, W)
+    _call("glrgtv_pixel_rstd", x, B, C, nsub, H * W, float(eps), x, rs)
+    return rs
+
+
+def dwconv_gate(h: Tensor, rs: Tensor, w9: Tensor, top: Optional[Tensor] = None, bot: Optional[Tensor] = None) -> Tensor:
+    """h [B,2Hd,H,W], rs [B,nsub,H,W], w9 [2Hd,9], top / bot [B,2Hd,W] scaled neighbour rows or None -> u [B,Hd,H,W]
+    = sigmoid(g) g v with g | v = the two halves of dw3x3_replicate(rs * h); glrgtv_dwconv_gate"""
+    _chk(h, rs, w9, *[t for t in (top, bot) if t is not None])
+    h, rs, w9 = _c(h), _c(rs), _c(w9)
+    B, C2, H, W = h.shape
+    if rs.shape != (B, rs.shape[1], H, W) or w9.shape != (C2, 9) or any(t is not None and t.shape != (B, C2, W) for t in (top, bot)):
+        raise RuntimeError("dwconv_gate: inconsistent shapes")
+    u = h.new_empty(B, C2 // 2, H, W)
+    _call("glrgtv_dwconv_gate", h, B, C2 // 2, rs.shape[1], H, W, h, rs, w9, _c(top) if top is not None else None,
+          _c(bot) if bot is not None else None, u)
+    return u
 
 
 # ---- space-to-depth in front of the 2x2 stride-2 projection (torch.pixel_unshuffle order), and its inverse

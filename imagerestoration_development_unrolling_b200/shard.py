@@ -90,6 +90,22 @@ def exchange_row_halos(strip: torch.Tensor, halo: int, rank: int, world: int, gr
     return torch.cat(parts, dim=-2), (halo if top is not None else 0), (halo if bot is not None else 0)
 
 
+def exchange_rows(first: torch.Tensor, last: torch.Tensor, rank: int, world: int, group=None):
+    """Send this strip's `first` row (any shape) to the rank above and its `last` row to the rank below; returns
+    (the upper neighbour's last row, the lower neighbour's first row), None at the true image border."""
+    ops, top, bot = [], None, None
+    if rank > 0:
+        top = torch.empty_like(first)
+        ops += [dist.P2POp(dist.isend, first, rank - 1, group), dist.P2POp(dist.irecv, top, rank - 1, group)]
+    if rank < world - 1:
+        bot = torch.empty_like(last)
+        ops += [dist.P2POp(dist.isend, last, rank + 1, group), dist.P2POp(dist.irecv, bot, rank + 1, group)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return top, bot
+
+
 def sharded_block_forward(block: Callable[[torch.Tensor], torch.Tensor], strip: torch.Tensor, rank: int, world: int,
                           halo: int = BLOCK_HALO_ROWS, group=None) -> torch.Tensor:
     """Run one filter block on this rank's row strip of a spatially sharded feature map: halo exchange with the two
@@ -198,13 +214,24 @@ class ShardedMultiScaleFilter:
 
     ALIGN = 16
 
-    def __init__(self, model, rank: int, world: int, group=None, block_forward=None):
+    def __init__(self, model, rank: int, world: int, group=None, block_forward=None, cnn_kernels="auto"):
+        """cnn_kernels: "auto" = libglrgtv's LocalNonLinearBlock kernels (host_cnn.py) for CUDA strips under no_grad, the
+        PyTorch modules otherwise; None = always the modules; or an object with pixel_rstd / dwconv_gate (the CPU tests)."""
         self.model, self.rank, self.world, self.group = model, rank, world, group
+        self.cnn_kernels = cnn_kernels
         self.block_forward = block_forward or (lambda blk, strip, scale: sharded_block_forward_staged(blk, strip, rank, world, group))
 
     # -- pieces of the host CNN
     def nonlinear_block(self, blk, x: torch.Tensor) -> torch.Tensor:
         """LocalNonLinearBlock (V1X0:951-964) on a strip; only its depthwise 3x3 needs neighbour rows."""
+        kern = self.cnn_kernels
+        if isinstance(kern, str):
+            from . import host_cnn
+            kern = host_cnn.CudaCnnKernels() if (x.is_cuda and not torch.is_grad_enabled()) else None
+        if kern is not None:
+            from . import host_cnn
+            ex = (lambda first, last: exchange_rows(first, last, self.rank, self.world, self.group)) if self.world > 1 else None
+            return host_cnn.nonlinear_block_forward(blk, x, kern, ex)
         ll = blk.local_linear
         h = ll.channels_linear_op(blk.norm(x))
         gate, val = conv3x3_on_strip(ll.channels_local_linear_op, h, self.rank, self.world, self.group).chunk(2, dim=1)

@@ -253,6 +253,21 @@ int glrgtv_proj_gemm(int transpose_w, int batch, int M, int N, int K, const floa
  * K % 48 == 0) or (K % 96 == 0, M % 48 == 0); GLRGTV_ERR_UNSUPPORTED otherwise. */
 int glrgtv_proj_wgrad(int batch, int M, int N, int K, const float* gY, const float* X, float* gW, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Host CNN, inference forward: the memory-bound pieces of LocalNonLinearBlock (V1X0:911-964).
+ * The caller does the two 1x1 convolutions as GEMMs (norm weight folded into the first, skip weights into the second).
+ *
+ * glrgtv_pixel_rstd: CustomLayerNorm's per-pixel scale (V1X0:918-925).  x [B,C,HW] -> rs [B,nsub,HW],
+ *   rs = 1 / sqrt(var + eps), var = unbiased variance over the C/nsub channels of each sub-net.  HW % 4 == 0.
+ * glrgtv_dwconv_gate: LocalGatedLinearBlock's depthwise 3x3 (replicate padded) and gate (V1X0:938-947) on the
+ *   un-normalised 1x1 output h [B,2Hd,H,W]:  m = dw3x3(rs * h);  u [B,Hd,H,W] = sigmoid(g) * g * v with g = m[:, :Hd],
+ *   v = m[:, Hd:].  w9 [2Hd,9] = the convolution weight [2Hd,1,3,3].  top / bot [B,2Hd,W]: the ALREADY SCALED rows
+ *   above / below a row strip of a spatially sharded image, or NULL at the true image border (replicate).  W % 4 == 0.
+ * ---------------------------------------------------------------------------------------------- */
+int glrgtv_pixel_rstd(int B, int C, int nsub, long HW, float eps, const float* x, float* rs, void* stream);
+int glrgtv_dwconv_gate(int B, int Hd, int nsub, int H, int W, const float* h, const float* rs, const float* w9,
+                       const float* top, const float* bot, float* u, void* stream);
+
 /* Space-to-depth in front of the 2x2 stride-2 projection (patchs_features_extraction01[0], V1X0:593-603) and its inverse:
  * inverse == 0: x [planes,H,W] -> y [planes*4,H/2,W/2], y[p*4 + dy*2 + dx, h, w] = x[p, 2h+dy, 2w+dx] (pixel_unshuffle order);
  * inverse == 1: the other way round (x is the deep tensor).  `planes` = B*C; W % 8 == 0, H even, 16-byte aligned. */

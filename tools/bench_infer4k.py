@@ -8,6 +8,7 @@ The four LocalLowpassFilteringBlock of the v13 model run (no_grad) on the featur
 strips (boundaries at even rows) and each block does one 26-row NCCL halo exchange (shard.sharded_block_forward).
 `--staged`: one 8-row exchange per solver stage instead.  `--model`: the WHOLE v13 network (host CNN on strips with one
 exchanged row per 3x3 convolution + the staged filter blocks, shard.ShardedMultiScaleFilter) on the 3-channel image.
+`--torch-cnn`: with --model, keep the LocalNonLinearBlocks on the PyTorch modules instead of host_cnn.py's kernels.
 `--steps K --warmup W` (default 5 / 3).
 Prints one JSON line: Mpix/s of the network input (8.29 Mpix per image), max over ranks of the CUDA-event time."""
 import json
@@ -54,7 +55,7 @@ def main():
                                              num_blocks=[4, 6, 6, 8], num_blocks_out=4).to(dev).eval()
         a, b = shard.strip_bounds(H0, world, align=16)[rank]
         img = torch.rand(1, 3, b - a, W0, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
-        ex = shard.ShardedMultiScaleFilter(net, rank, world)
+        ex = shard.ShardedMultiScaleFilter(net, rank, world, cnn_kernels=None if "--torch-cnn" in sys.argv else "auto")
 
     def run():
         with torch.no_grad():
@@ -85,7 +86,8 @@ def main():
                           "ms_per_image": ms, "scaling": "strong", "dtype": "f32", "data": "synthetic",
                           "steps": steps, "warmup": warmup,
                           "config": {"workload": ("whole v13 network, one 3840x2160 image, row strips, one row per 3x3 convolution + 8-row halo "
-                                                  "exchange per solver stage") if whole else
+                                                  "exchange per solver stage, LocalNonLinearBlocks on "
+                                                  + ("the PyTorch modules" if "--torch-cnn" in sys.argv else "libglrgtv kernels + cuBLAS")) if whole else
                                      "v13 four filter blocks, forward, feature maps of one 3840x2160 image, row strips, "
                                      + ("8-row halo exchange per solver stage" if staged else "26-row halo exchange per block")}}))
     if world > 1:
