@@ -27,6 +27,14 @@ def to_ubyte(x: torch.Tensor) -> torch.Tensor:
     return torch.round(x * 255.0).clamp_(0.0, 255.0)
 
 
+def inference_executor(model, rank: int = 0, world: int = 1, group=None):
+    """The network as a callable for inference (`restore_image(inference_executor(model), noisy)`): same results as
+    `model(...)`, with the host CNN's LocalNonLinearBlocks on libglrgtv's kernels (host_cnn.py) and, for world > 1, the image
+    cut into row strips across ranks (shard.ShardedMultiScaleFilter; pass this rank's strip)."""
+    from . import shard
+    return shard.ShardedMultiScaleFilter(model, rank, world, group)
+
+
 @torch.no_grad()
 def restore_image(model, noisy: torch.Tensor) -> torch.Tensor:
     """noisy [1,3,h,w] float32 on the model's device -> restored image quantised to 0..255 (float tensor, [1,3,h,w])"""
