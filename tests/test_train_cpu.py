@@ -1,0 +1,132 @@
+"""Training-loop callers (train.py) on CPU: model factory, the reference's checkpoint layout and resume rule,
+bit-exact resume, and the gloo world-2 loop.  The filter blocks have no CPU path, so the loop runs a small stand-in model with
+the same encode / decode / forward surface, registered through MODEL_TYPES."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+from imagerestoration_development_unrolling_b200 import train as T
+
+
+class TinyNet(nn.Module):
+    def __init__(self, width=4):
+        super().__init__()
+        self.enc = nn.Conv2d(3, width, 3, padding=1, padding_mode="replicate", bias=False)
+        self.dec = nn.Conv2d(width, 3, 1, bias=False)
+
+    def encode(self, img):
+        return (torch.tanh(self.enc(img)),)
+
+    def decode(self, coefs):
+        return self.dec(coefs[0])
+
+    def forward(self, img):
+        return self.decode(self.encode(img))
+
+
+def _conf(root, total, every=3, bs=2):
+    return {"name": "unit", "manual_seed": 2204, "path": {"root_dir": str(root)},
+            "datasets": {"train": {"type": "SyntheticNoisyPatches", "dataset_args": {"patch_size": 8, "lambda_noise": 25.0, "max_num_patchs": 64},
+                                   "dataloader_args": {"batch_size": bs}}},
+            "model": {"type": "tiny", "args": {"width": 4}},
+            "train": {"total_iters": total, "checkpoint_every": every, "log_every": 0, "optimizer": {"lr": 1e-2}}}
+
+
+@pytest.fixture(autouse=True)
+def _register():
+    T.MODEL_TYPES["tiny"] = TinyNet
+    yield
+    T.MODEL_TYPES.pop("tiny", None)
+
+
+def test_model_factory_defaults_and_errors():
+    m = T.build_model({"type": "AbtractMultiScaleGraphFilter", "args": {"dims": [8, 8, 8, 8], "hidden_dims": [8, 8, 8, 8], "ngraphs": [2, 2, 2, 2],
+                                                                        "num_blocks": [1, 1, 1, 1], "num_blocks_out": 1}})
+    assert len(m.encoder_scale_00) == 1 and m.linear_output.out_channels == 3
+    assert T.V13_ARGS["ngraphs"] == [8, 16, 16, 32] and T.V13_ARGS["num_blocks"] == [4, 6, 6, 8]
+    with pytest.raises(KeyError, match="known types"):
+        T.build_model({"type": "nope"})
+
+
+def test_checkpoint_layout_and_latest(tmp_path):
+    m = TinyNet()
+    opt, sch = T.build_optimizer(m)
+    assert T.checkpoint_name(0, 330000) == "checkpoints_epoch00_iter0330k.pt"          # the file the reference script mentions
+    T.save_checkpoint(str(tmp_path), 0, 5000, m, opt, sch)
+    p = T.save_checkpoint(str(tmp_path), 0, 10000, m, opt, sch)
+    assert T.latest_checkpoint(str(tmp_path)) == p and T.latest_checkpoint(str(tmp_path / "missing")) is None
+    state = torch.load(p, weights_only=False)
+    assert set(state) == {"i", "model", "optimizer", "lr_scheduler"} and state["i"] == 10000
+    m2 = TinyNet()
+    opt2, sch2 = T.build_optimizer(m2)
+    assert T.load_checkpoint(p, m2, opt2, sch2) == 10000
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+def test_lr_schedule_follows_the_reference():
+    opt, sch = T.build_optimizer(TinyNet(), {"step_every": 2, "n_steps": 3, "cosine_iters": 10})
+    lrs = []
+    for _ in range(8):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sch.step()
+    g = 0.5 ** 0.25
+    assert lrs[:6] == pytest.approx([4e-4, 4e-4, 4e-4 * g, 4e-4 * g, 4e-4 * g * g, 4e-4 * g * g])
+    assert lrs[6] == pytest.approx(5e-5) and lrs[7] < lrs[6]                             # the cosine phase restarts from its own base lr
+
+
+def test_sampler_shards_and_resumes():
+    a = list(T.ResumableShardedSampler(20, 2, rank=0, world=2))
+    b = list(T.ResumableShardedSampler(20, 2, rank=1, world=2))
+    assert a[:2] == [[0, 1], [4, 5]] and b[:2] == [[2, 3], [6, 7]] and len(a) == 5
+    assert list(T.ResumableShardedSampler(20, 2, rank=1, world=2, start_batch=3)) == b[3:]
+    d = T.SyntheticNoisyPatches(patch_size=8, max_num_patchs=4)
+    n0, c0 = d[1]
+    n1, c1 = d[1]
+    assert torch.equal(n0, n1) and n0.shape == (8, 8, 3) and float((n0 - c0).std()) == pytest.approx(25 / 255, rel=0.2)
+
+
+def test_resume_is_bit_exact(tmp_path):
+    losses = {}
+    straight = T.train(_conf(tmp_path / "a", total=6), torch.device("cpu"), on_step=lambda i, l: losses.setdefault(i, l))
+    assert sorted(losses) == list(range(6)) and losses[5] < losses[0]
+    T.train(_conf(tmp_path / "b", total=3), torch.device("cpu"))
+    seen = []
+    resumed = T.train(_conf(tmp_path / "b", total=6), torch.device("cpu"), on_step=lambda i, l: seen.append(i))
+    assert seen == [3, 4, 5]
+    for a, b in zip(straight.state_dict().values(), resumed.state_dict().values()):
+        assert torch.equal(a, b)
+
+
+def _worker(rank, world, port, root, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    T.MODEL_TYPES["tiny"] = TinyNet
+    m = T.train(_conf(root, total=4, every=2), torch.device("cpu"))
+    q.put((rank, [v.numpy().copy() for v in m.state_dict().values()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_stay_in_sync_and_rank0_checkpoints(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    for a, b in zip(res[0], res[1]):
+        assert (a == b).all()
+    folder = T.checkpoints_folder(_conf(tmp_path, 4))
+    assert os.listdir(folder) == ["checkpoints_epoch00_iter0000k.pt"]
+    assert torch.load(os.path.join(folder, os.listdir(folder)[0]), weights_only=False)["i"] == 3
