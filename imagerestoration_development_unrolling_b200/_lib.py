@@ -102,6 +102,8 @@ _SIGS = {
     "glrgtv_space_to_depth": (C.c_int, [C.c_int, C.c_long, C.c_int, C.c_int, fp, fp, fp]),
     "glrgtv_pixel_rstd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, fp, fp, fp]),
     "glrgtv_dwconv_gate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp, fp]),
+    "glrgtv_dwconv_gate_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp, fp, fp]),
+    "glrgtv_pixel_norm_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_long, fp, fp, fp, fp, fp, fp, fp]),
     "glrgtv_proj_wgrad": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]),
     "glrgtv_block_fwd": (C.c_int, [_P(Shape), _P(BlockParams), fp, fp, fp, fp, _P(BlockSaved), fp]),
     "glrgtv_block_fwd_stage": (C.c_int, [C.c_int, _P(Shape), _P(BlockParams), fp, fp, fp, fp, _P(BlockSaved), C.c_int, C.c_int, fp]),

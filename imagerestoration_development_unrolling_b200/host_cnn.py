@@ -26,6 +26,14 @@ class CudaCnnKernels:
         from . import ops
         return ops.dwconv_gate(h, rs, w9, top, bot)
 
+    def dwconv_gate_bwd(self, h, rs, w9, gu):
+        from . import ops
+        return ops.dwconv_gate_bwd(h, rs, w9, gu)
+
+    def pixel_norm_bwd(self, x, rs, gx1, gout, s0, nsub):
+        from . import ops
+        return ops.pixel_norm_bwd(x, rs, gx1, gout, s0, nsub)
+
 
 def folded_weights(blk) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """(W1' [nsub, 2Hd/nsub, C/nsub], w_dw [2Hd, 9], s1 W2 [nsub, C/nsub, Hd/nsub], s0 [1]) of a LocalNonLinearBlock"""
@@ -61,3 +69,57 @@ def nonlinear_block_forward(blk, x: torch.Tensor, kernels=None,
     u = kernels.dwconv_gate(h, rs, w9, top, bot)                                        # [B, Hd, H, W]
     y = torch.matmul(w2, u.view(B, nsub, -1, H * W)).view(B, C, H, W)
     return torch.addcmul(y, x, s0)
+
+
+# ---------------------------------------------------------------------------------------------------- training
+class _NonLinearBlockFn(torch.autograd.Function):
+    """LocalNonLinearBlock forward + backward on the kernels.  Saves x, rs, h (un-normalised 1x1 output) and u - the module's
+    autograd keeps the normalised input, the padded hidden tensor, both halves, the sigmoid and two products besides."""
+
+    @staticmethod
+    def forward(ctx, x, w_norm, w_lin, w_dw, w_out, skip, nsub, kernels):
+        B, C, H, W = x.shape
+        x = x.contiguous()
+        w1 = (w_lin.reshape(nsub, w_lin.shape[0] // nsub, w_lin.shape[1]) * w_norm.reshape(nsub, 1, -1)).contiguous()
+        w2 = w_out.reshape(nsub, w_out.shape[0] // nsub, w_out.shape[1])
+        w9 = w_dw.reshape(-1, 9).contiguous()
+        rs = kernels.pixel_rstd(x, nsub, NORM_EPS)
+        h = torch.matmul(w1, x.view(B, nsub, C // nsub, H * W)).view(B, -1, H, W)
+        u = kernels.dwconv_gate(h, rs, w9, None, None)
+        y = torch.matmul(w2 * skip[1], u.view(B, nsub, -1, H * W)).view(B, C, H, W)
+        ctx.save_for_backward(x, rs, h, u, w_norm, w_lin, w_dw, w_out, skip)
+        ctx.nsub, ctx.kernels = nsub, kernels
+        return torch.addcmul(y, x, skip[0:1])
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, rs, h, u, w_norm, w_lin, w_dw, w_out, skip = ctx.saved_tensors
+        nsub, kernels = ctx.nsub, ctx.kernels
+        B, C, H, W = x.shape
+        N = H * W
+        gout = gout.contiguous()
+        w1 = w_lin.reshape(nsub, w_lin.shape[0] // nsub, w_lin.shape[1])
+        wn = w_norm.reshape(nsub, 1, -1)
+        w1f = (w1 * wn).contiguous()
+        w2 = w_out.reshape(nsub, w_out.shape[0] // nsub, w_out.shape[1])
+        g4, u4, x4 = gout.view(B, nsub, C // nsub, N), u.view(B, nsub, -1, N), x.view(B, nsub, C // nsub, N)
+        # out = s0 x + s1 W2 u
+        gw2_raw = torch.matmul(g4, u4.transpose(-1, -2)).sum(0)                              # [nsub, C/nsub, Hd/nsub] = sum gout u^T
+        g_skip = torch.stack([torch.dot(gout.reshape(-1), x.reshape(-1)), (gw2_raw * w2).sum()])
+        gu = torch.matmul((w2 * skip[1]).transpose(-1, -2), g4).view(B, -1, H, W)            # [B, Hd, H, W]
+        gh, gw9 = kernels.dwconv_gate_bwd(h, rs, w_dw.reshape(-1, 9).contiguous(), gu)
+        gh4 = gh.view(B, nsub, -1, N)
+        gw1f = torch.matmul(gh4, x4.transpose(-1, -2)).sum(0)                                # [nsub, 2Hd/nsub, C/nsub]
+        gx1 = torch.matmul(w1f.transpose(-1, -2), gh4).view(B, C, H, W)
+        gx = kernels.pixel_norm_bwd(x, rs, gx1, gout, skip[0:1], nsub)
+        return (gx, (gw1f * w1).sum(1).reshape(w_norm.shape), (gw1f * wn).reshape(w_lin.shape), gw9.reshape(w_dw.shape),
+                (gw2_raw * skip[1]).reshape(w_out.shape), g_skip, None, None)
+
+
+def nonlinear_block_train(blk, x: torch.Tensor, kernels=None) -> torch.Tensor:
+    """LocalNonLinearBlock(x) with autograd through the kernels (opt-in: the drop-in module's own forward stays PyTorch until this
+    path has been measured on the GPU).  Whole images (training patches), W % 4 == 0."""
+    ll = blk.local_linear
+    return _NonLinearBlockFn.apply(x, blk.norm.weighted_transform.weight, ll.channels_linear_op.weight.flatten(1),
+                                   ll.channels_local_linear_op.weight, ll.project_out.weight.flatten(1), blk.skip_weight,
+                                   blk.norm.nsubnets, kernels or CudaCnnKernels())

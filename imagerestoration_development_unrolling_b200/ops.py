@@ -455,6 +455,26 @@ def dwconv_gate(h: Tensor, rs: Tensor, w9: Tensor, top: Optional[Tensor] = None,
     return u
 
 
+def dwconv_gate_bwd(h: Tensor, rs: Tensor, w9: Tensor, gu: Tensor) -> Tuple[Tensor, Tensor]:
+    """(gh [B,2Hd,H,W], gw9 [2Hd,9]) from gu = dL/du; glrgtv_dwconv_gate_bwd"""
+    _chk(h, rs, w9, gu)
+    h, rs, w9, gu = _c(h), _c(rs), _c(w9), _c(gu)
+    B, C2, H, W = h.shape
+    gM, gh, gw9 = torch.empty_like(h), torch.empty_like(h), torch.zeros_like(w9)
+    _call("glrgtv_dwconv_gate_bwd", h, B, C2 // 2, rs.shape[1], H, W, h, rs, w9, gu, gM, gh, gw9)
+    return gh, gw9
+
+
+def pixel_norm_bwd(x: Tensor, rs: Tensor, gx1: Tensor, gout: Tensor, s0: Tensor, nsub: int) -> Tensor:
+    """gx = s0 gout + gx1 - <gx1,x>_c rs^2 (x - mean_c x)/(c-1); glrgtv_pixel_norm_bwd"""
+    _chk(x, rs, gx1, gout, s0)
+    x, rs, gx1, gout, s0 = _c(x), _c(rs), _c(gx1), _c(gout), _c(s0)
+    B, C, H, W = x.shape
+    gx = torch.empty_like(x)
+    _call("glrgtv_pixel_norm_bwd", x, B, C, nsub, H * W, x, rs, gx1, gout, s0, gx)
+    return gx
+
+
 # ---- space-to-depth in front of the 2x2 stride-2 projection (torch.pixel_unshuffle order), and its inverse
 @torch.library.custom_op(f"{_NS}::space_to_depth", mutates_args=())
 def space_to_depth(x: Tensor, inverse: bool) -> Tensor:

@@ -268,6 +268,17 @@ int glrgtv_pixel_rstd(int B, int C, int nsub, long HW, float eps, const float* x
 int glrgtv_dwconv_gate(int B, int Hd, int nsub, int H, int W, const float* h, const float* rs, const float* w9,
                        const float* top, const float* bot, float* u, void* stream);
 
+/* Backward of the two pieces above (training; host_cnn.py's autograd function), whole images only.
+ * glrgtv_dwconv_gate_bwd: gu [B,Hd,H,W] = dL/du -> gh [B,2Hd,H,W] = dL/dh (h as given to the forward), gw9 [2Hd,9] +=
+ *   depthwise weight gradient (ACCUMULATES: the caller zeroes it); gM [B,2Hd,H,W] is scratch (dL/d conv output).
+ * glrgtv_pixel_norm_bwd: the input gradient of the block: gx [B,C,HW] = s0 gout + gx1 - <gx1,x>_c rs^2 (x - mean_c x)/(c-1),
+ *   where gx1 = W1'^T gh is the caller's GEMM (gradient through the 1x1) and the last term is the gradient through rs;
+ *   s0 points at the block's first skip weight on the device. */
+int glrgtv_dwconv_gate_bwd(int B, int Hd, int nsub, int H, int W, const float* h, const float* rs, const float* w9,
+                           const float* gu, float* gM, float* gh, float* gw9, void* stream);
+int glrgtv_pixel_norm_bwd(int B, int C, int nsub, long HW, const float* x, const float* rs, const float* gx1,
+                          const float* gout, const float* s0, float* gx, void* stream);
+
 /* Space-to-depth in front of the 2x2 stride-2 projection (patchs_features_extraction01[0], V1X0:593-603) and its inverse:
  * inverse == 0: x [planes,H,W] -> y [planes*4,H/2,W/2], y[p*4 + dy*2 + dx, h, w] = x[p, 2h+dy, 2w+dx] (pixel_unshuffle order);
  * inverse == 1: the other way round (x is the deep tensor).  `planes` = B*C; W % 8 == 0, H even, 16-byte aligned. */

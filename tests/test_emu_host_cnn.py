@@ -22,6 +22,19 @@ class EmuCnnKernels:
         return u
 
 
+    def dwconv_gate_bwd(self, h, rs, w9, gu):
+        B, C2, H, W = h.shape
+        gM, gh, gw9 = torch.full_like(h, float("nan")), torch.full_like(h, float("nan")), torch.zeros_like(w9)
+        E.call("glrgtv_dwconv_gate_bwd", B, C2 // 2, rs.shape[1], H, W, h.contiguous(), rs, w9, gu.contiguous(), gM, gh, gw9, None)
+        return gh, gw9
+
+    def pixel_norm_bwd(self, x, rs, gx1, gout, s0, nsub):
+        B, C, H, W = x.shape
+        gx = torch.full_like(x, float("nan"))
+        E.call("glrgtv_pixel_norm_bwd", B, C, nsub, H * W, x, rs, gx1.contiguous(), gout.contiguous(), s0.contiguous(), gx, None)
+        return gx
+
+
 def _block(dim, hidden, nsub, seed):
     torch.manual_seed(seed)
     blk = M.LocalNonLinearBlock(dim, hidden, nsub).eval()
@@ -91,3 +104,34 @@ def test_argument_checks():
         E.call("glrgtv_pixel_rstd", 1, 4, 4, 8, 1e-5, x, x, None)                 # one channel per sub-net: no variance
     with pytest.raises(RuntimeError):
         E.call("glrgtv_dwconv_gate", 1, 2, 1, 2, 6, x, x, x, None, None, x, None)  # W % 4 != 0
+
+
+@pytest.mark.parametrize("dim,hidden,nsub,B,H,W", [
+    (8, 12, 1, 2, 9, 12),
+    (12, 8, 2, 1, 70, 20),
+    (6, 4, 1, 1, 1, 4),        # one row, one quad: every padded tap folds back onto the pixel itself
+    (6, 4, 1, 1, 2, 8),
+    (16, 16, 4, 1, 33, 8),
+    (4, 2, 1, 1, 3, 260),
+])
+def test_nonlinear_block_gradients_match_autograd(dim, hidden, nsub, B, H, W):
+    """input and all six parameter gradients of the kernel path against autograd through the module (double precision)"""
+    blk = _block(dim, hidden, nsub, seed=H + 1)
+    x = (torch.randn(B, dim, H, W, generator=torch.Generator().manual_seed(W + 1)) * 2 + 0.5).requires_grad_(True)
+    gout = torch.randn(B, dim, H, W, generator=torch.Generator().manual_seed(3))
+    params = [blk.norm.weighted_transform.weight, blk.local_linear.channels_linear_op.weight, blk.local_linear.channels_local_linear_op.weight,
+              blk.local_linear.project_out.weight, blk.skip_weight]
+    out = host_cnn.nonlinear_block_train(blk, x, EmuCnnKernels())
+    got = torch.autograd.grad(out, [x] + params, gout)
+    import copy
+    ref_blk = copy.deepcopy(blk).double()
+    xd = x.detach().double().requires_grad_(True)
+    rp = [ref_blk.norm.weighted_transform.weight, ref_blk.local_linear.channels_linear_op.weight, ref_blk.local_linear.channels_local_linear_op.weight,
+          ref_blk.local_linear.project_out.weight, ref_blk.skip_weight]
+    ref_out = ref_blk(xd)
+    ref = torch.autograd.grad(ref_out, [xd] + rp, gout.double())
+    assert float((out.detach().double() - ref_out.detach()).abs().max()) < 2e-5 * float(ref_out.detach().abs().max())
+    for name, g, r in zip(["x", "norm", "linear", "depthwise", "project_out", "skip"], got, ref):
+        assert g.shape == r.shape, name
+        assert torch.isfinite(g).all(), name
+        assert float((g.double() - r).norm()) < 2e-5 * float(r.norm()) + 1e-9, name
