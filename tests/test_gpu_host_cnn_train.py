@@ -1,6 +1,5 @@
 """LocalNonLinearBlock forward + backward on libglrgtv's kernels (host_cnn.nonlinear_block_train, opt-in) against autograd through
-the module on the GPU.  The kernels are pinned on CPU by tests/test_emu_host_cnn.py (emulation build, double-precision autograd);
-this file sorts last on purpose: the path is opt-in and its first GPU run is the round-end run."""
+the module (double precision) on the GPU.  The same comparison runs on CPU on the emulation build (tests/test_emu_host_cnn.py)."""
 import copy
 
 import pytest
