@@ -230,6 +230,18 @@ class LocalGatedLinearBlock(nn.Module):
         return self.project_out(torch.sigmoid(gate) * gate * val)
 
 
+HOST_CNN_KERNELS = False
+
+
+def set_host_cnn_kernels(on: bool) -> bool:
+    """Opt-in: run every LocalNonLinearBlock of the host CNN on libglrgtv's kernels (host_cnn.py: forward under no_grad, forward +
+    backward under autograd) instead of the PyTorch op sequence.  Same results (tests/test_gpu_host_cnn*.py); off by default until
+    the training path has been timed.  Returns the previous setting.  Not used while torch.compile is tracing."""
+    global HOST_CNN_KERNELS
+    prev, HOST_CNN_KERNELS = HOST_CNN_KERNELS, bool(on)
+    return prev
+
+
 class LocalNonLinearBlock(nn.Module):
     """V1X0:951-964."""
 
@@ -240,6 +252,12 @@ class LocalNonLinearBlock(nn.Module):
         self.skip_weight = Parameter(torch.tensor([1.0, 1.0], dtype=torch.float32))
 
     def forward(self, x):
+        if (HOST_CNN_KERNELS and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[-1] % 4 == 0
+                and not torch.compiler.is_compiling()):
+            from . import host_cnn
+            if torch.is_grad_enabled():
+                return host_cnn.nonlinear_block_train(self, x)
+            return host_cnn.nonlinear_block_forward(self, x)
         return self.skip_weight[0] * x + self.skip_weight[1] * self.local_linear(self.norm(x))
 
 

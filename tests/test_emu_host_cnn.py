@@ -135,3 +135,18 @@ def test_nonlinear_block_gradients_match_autograd(dim, hidden, nsub, B, H, W):
         assert g.shape == r.shape, name
         assert torch.isfinite(g).all(), name
         assert float((g.double() - r).norm()) < 2e-5 * float(r.norm()) + 1e-9, name
+
+
+def test_switch_is_a_noop_for_cpu_tensors():
+    """the opt-in switch only reroutes CUDA float32 inputs; CPU tensors keep the PyTorch op sequence (the host CNN is not the
+    library's hot path, so it may run anywhere the reference's does)"""
+    blk = _block(8, 8, 1, seed=2)
+    x = torch.randn(1, 8, 6, 8)
+    with torch.no_grad():
+        ref = blk(x)
+        prev = M.set_host_cnn_kernels(True)
+        try:
+            got = blk(x)
+        finally:
+            M.set_host_cnn_kernels(prev)
+    assert prev is False and torch.equal(got, ref)

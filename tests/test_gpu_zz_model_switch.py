@@ -1,0 +1,40 @@
+"""set_host_cnn_kernels(True): the whole drop-in network with every LocalNonLinearBlock on libglrgtv's kernels equals the network
+on the PyTorch op sequence, forward (no_grad), and forward + backward (all 359-entry-layout gradients).  The pieces are tested on
+the GPU one block at a time in test_gpu_host_cnn*.py; this whole-network switch sorts last because its first GPU run is the
+round-end run."""
+import pytest
+import torch
+
+from tests.util import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def test_switch_keeps_outputs_and_gradients():
+    from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
+    from tests.test_gpu_model import CFG
+    torch.manual_seed(4)
+    m = M.AbtractMultiScaleGraphFilter(**CFG).cuda()
+    img = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(1)).cuda()
+    gout = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(2)).cuda()
+    params = list(m.parameters())
+
+    def run():
+        out = m(img)
+        return out.detach(), torch.autograd.grad(out, params, gout)
+
+    prev = M.set_host_cnn_kernels(False)
+    try:
+        ref_out, ref_g = run()
+        M.set_host_cnn_kernels(True)
+        out, g = run()
+        with torch.no_grad():
+            inf = m(img)
+    finally:
+        M.set_host_cnn_kernels(prev)
+    assert rel(out, ref_out) < 1e-5 and rel(inf, ref_out) < 1e-5
+    names = [n for n, _ in m.named_parameters()]
+    for n, a, b in zip(names, g, ref_g):
+        # the filter blocks' thresholds can flip on 1e-7 input differences: same tolerances as the cross-implementation block tests
+        tol = 5e-2 if "gamma" in n else 5e-3
+        assert float((a - b).norm()) <= tol * float(b.norm()) + 1e-7, n
