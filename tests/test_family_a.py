@@ -121,3 +121,68 @@ def test_iteration_and_window_sweep_against_generalised_oracle(window, schedule)
     wT, wL = m.GTVmodule00.extract_edge_weights(feat.to(dev)), m.GLRmodule00.extract_edge_weights(feat.to(dev))
     out = m.unrolled_solve(y.to(dev), wT, wL, schedule)
     assert rel(out, ref) < 1e-4, rel(out, ref)
+
+
+# ---- the loop-generalised solver pinned at the reference's other fixed points: v1 = schedule (2, 4), full 3x3 / 5x5
+#      windows, no stats convolutions (= identity stats: p01 = 1, p02a = p02b = p03 = 0)
+def _v1_case(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    one, zero = torch.ones(1, dtype=torch.float64), torch.zeros(1, dtype=torch.float64)
+    for mod in ("GTVmodule00.", "GLRmodule00."):
+        sd.update({mod + "stats_kernel_p01": one, mod + "stats_kernel_p02a": zero, mod + "stats_kernel_p02b": zero, mod + "stats_kernel_p03": zero})
+    return g, sd
+
+
+def _v1_solve(g, sd):
+    edges = O.window_edges(g["window"].tolist())
+    B, _, H, W = g["x"].shape
+    G, F = sd["GTVmodule00.multiM"].shape
+    feats = g["feats"].reshape(B, G, F, H, W)
+    wT, wL = O.edge_weights(feats, sd["GTVmodule00.multiM"], edges), O.edge_weights(feats, sd["GLRmodule00.multiM"], edges)
+    out = O.unrolled_admm_solve(sd, g["x"][:, None].expand(B, G, 3, H, W), wT, wL, edges, schedule=(2, 4))
+    return (out * g["score"][:, :, None]).sum(dim=1)
+
+
+@pytest.mark.parametrize("name,n_edges", [("v1_mixturegtv_full3", 8), ("v1_mixturegtv_full5", 24)])
+def test_oracle_generalised_solver_matches_reference_v1(golden_dir, name, n_edges):
+    """outputs and the gradients of every graph parameter (the CNN outputs are inputs here, so these are total derivatives)"""
+    g, sd = _v1_case(golden_dir, name)
+    assert len(O.window_edges(g["window"].tolist())) == n_edges
+    graph = ("ro00", "muys00", "gamma00", "alphaCGD", "betaCGD", "GTVmodule00.multiM", "GLRmodule00.multiM")
+    for k in graph:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    out = _v1_solve(g, sd)
+    assert rel(out, g["out"]) < 1e-13
+    grads = torch.autograd.grad(out, [sd[k] for k in graph], g["gout"])
+    for k, gr in zip(graph, grads):
+        ref = g["grad." + k]
+        if float(ref.abs().max()) == 0.0:
+            assert float(gr.abs().max()) == 0.0, k            # betaCGD rows 0 and 2: the first iteration of a solve has no momentum
+        else:
+            assert rel(gr, ref) < 1e-11, k
+
+
+def test_oracle_generalised_solver_matches_reference_glr_only(golden_dir):
+    """the GLR-only ablation (v13_no_orders_noGTV.GLR): schedule (3,), ro = 0, identity stats, exp(muys00), 3x3-cross window"""
+    z = np.load(os.path.join(golden_dir, "glr_only_g3_f4.npz"))
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    G, F = g["sd.GLRmodule00.multiM"].shape
+    B, C, H, W = g["x"].shape
+    graph = ("muys00", "alphaCGD", "betaCGD", "GLRmodule00.multiM")
+    p = {k: g["sd." + k].clone().requires_grad_(True) for k in graph}
+    one, zero = torch.ones(1, dtype=torch.float64), torch.zeros(1, dtype=torch.float64)
+    sd = {"alphaCGD": p["alphaCGD"], "betaCGD": p["betaCGD"], "muys00": p["muys00"].exp(), "ro00": torch.zeros(G, dtype=torch.float64),
+          "gamma00": torch.zeros(G, dtype=torch.float64), "GLRmodule00.multiM": p["GLRmodule00.multiM"],
+          "GTVmodule00.multiM": torch.ones(G, F, dtype=torch.float64)}
+    for mod in ("GTVmodule00.", "GLRmodule00."):
+        sd.update({mod + "stats_kernel_p01": one, mod + "stats_kernel_p02a": zero, mod + "stats_kernel_p02b": zero, mod + "stats_kernel_p03": zero})
+    edges = O.window_edges("cross3")
+    wL = O.edge_weights(g["feats"].reshape(B, G, F, H, W), sd["GLRmodule00.multiM"], edges)
+    out = O.unrolled_admm_solve(sd, g["x"].reshape(B, G, F, H, W), torch.zeros_like(wL), wL, edges, schedule=(3,)).reshape(B, C, H, W)
+    assert rel(out, g["out"]) < 1e-13
+    for k, gr in zip(graph, torch.autograd.grad(out, [p[k] for k in graph], g["gout"])):
+        ref = g["grad." + k]
+        mask = ref != 0
+        assert torch.equal(gr != 0, mask) and rel(gr[mask], ref[mask]) < 1e-11, k
