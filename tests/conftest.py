@@ -21,3 +21,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture
+def isolated_rng():
+    """Run a test on a forked copy of the global torch RNGs (CPU and CUDA): what it seeds or draws does not shift the random
+    inputs of the tests that run after it (several older tests draw from the global stream)."""
+    import torch
+    with torch.random.fork_rng():
+        yield

@@ -7,6 +7,8 @@ from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGT
 from imagerestoration_development_unrolling_b200 import host_cnn
 from tests import emu_harness as E
 
+pytestmark = pytest.mark.usefixtures("isolated_rng")
+
 
 class EmuCnnKernels:
     def pixel_rstd(self, x, nsub, eps):

@@ -9,7 +9,7 @@ import torch
 
 from tests.util import rel
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("isolated_rng")]
 
 
 def _block(dim, hidden, nsub, seed):

@@ -7,7 +7,7 @@ import torch
 
 from tests.util import rel
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("isolated_rng")]
 
 
 @pytest.mark.parametrize("dim,hidden,nsub,B,H,W", [(48, 96, 1, 2, 64, 64), (24, 16, 2, 3, 33, 8), (96, 192, 1, 1, 70, 52)])

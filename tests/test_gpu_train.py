@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("isolated_rng")]
 
 
 def _conf(root, total):

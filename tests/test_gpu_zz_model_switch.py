@@ -7,7 +7,7 @@ import torch
 
 from tests.util import rel
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("isolated_rng")]
 
 
 def test_switch_keeps_outputs_and_gradients():

@@ -12,6 +12,8 @@ from torch import nn
 
 from imagerestoration_development_unrolling_b200 import train as T
 
+pytestmark = pytest.mark.usefixtures("isolated_rng")
+
 
 class TinyNet(nn.Module):
     def __init__(self, width=4):
