@@ -8,9 +8,17 @@ from oracle import glr_gtv_oracle as O
 from imagerestoration_development_unrolling_b200 import _lib as L
 from tests import emu_harness as E
 
-torch.manual_seed(0)
 WINDOWS = ["cross3", "full3", "small5"]
 SHAPES = [(2, 2, 3, 5, 7), (1, 3, 6, 2, 2), (1, 1, 4, 1, 6), (1, 2, 2, 6, 1), (1, 1, 3, 4, 4)]
+
+
+@pytest.fixture(autouse=True)
+def _seed(request):
+    """every test draws from its own seeded stream: the data does not depend on which tests ran before"""
+    import zlib
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(zlib.crc32(request.node.nodeid.encode()))
+        yield
 
 
 def rel(a, b):
