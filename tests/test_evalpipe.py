@@ -55,3 +55,21 @@ def test_padding_rule():
         assert p.shape[-2] % 16 == 0 and p.shape[-1] % 16 == 0
         assert p.shape[-2] - h < 16 and p.shape[-1] - w < 16
         assert (h % 16 == 0) == (p.shape[-2] == h)
+
+
+def test_inference_executor_keeps_the_model_surface():
+    """evalpipe.inference_executor(model) is the reference's surface (encode / filtering / decode / enc_dec / call); on CPU tensors
+    the host CNN stays on the PyTorch modules, so enc_dec must reproduce the module exactly"""
+    import torch
+    from imagerestoration_development_unrolling_b200 import evalpipe, deep_multiscale_GGLR_GGTV_v1x0 as M
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(5)
+        m = M.AbtractMultiScaleGraphFilter(dims=[8, 8, 8, 8], hidden_dims=[8, 8, 8, 8], ngraphs=[2, 2, 2, 2], num_blocks=[1, 1, 1, 1], num_blocks_out=1).eval()
+        img = torch.rand(1, 3, 32, 48)
+    net = evalpipe.inference_executor(m)
+    for name in ("encode", "filtering", "decode", "enc_dec", "forward"):
+        assert callable(getattr(net, name))
+    with torch.no_grad():
+        assert torch.equal(net.enc_dec(img), m.enc_dec(img))
+        lat_a, lat_b = net.encode(img), m.encode(img)
+    assert len(lat_a) == 4 and all(torch.equal(a, b) for a, b in zip(lat_a, lat_b))
