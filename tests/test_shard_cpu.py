@@ -285,3 +285,24 @@ def test_sharded_model_rejects_unaligned_strips():
     m = _tiny_model()
     with pytest.raises(ValueError, match="multiples of 16"):
         shard.ShardedMultiScaleFilter(m, 0, 1).encode(torch.rand(1, 3, 40, 32))
+
+
+# ----------------------------------------------------------------------------------------------- partition properties
+def test_strip_bounds_properties():
+    """strips tile [0, H) in order, every boundary is a multiple of the alignment, heights differ by at most one unit"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(units=st.integers(1, 400), world=st.integers(1, 16), align=st.sampled_from([2, 16]))
+    def check(units, world, align):
+        H = units * align
+        b = shard.strip_bounds(H, world, align)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == H
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all(a % align == 0 and e % align == 0 and e >= a for a, e in b)
+        sizes = [(e - a) // align for a, e in b]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+    check()
+    with pytest.raises(ValueError):
+        shard.strip_bounds(30, 2, 16)

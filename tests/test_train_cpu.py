@@ -132,3 +132,21 @@ def test_two_ranks_stay_in_sync_and_rank0_checkpoints(tmp_path):
     folder = T.checkpoints_folder(_conf(tmp_path, 4))
     assert os.listdir(folder) == ["checkpoints_epoch00_iter0000k.pt"]
     assert torch.load(os.path.join(folder, os.listdir(folder)[0]), weights_only=False)["i"] == 3
+
+
+def test_sampler_partition_properties():
+    """over all ranks every global batch is covered exactly once, in order, and a resume point skips exactly the batches before it"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(n=st.integers(0, 300), bs=st.integers(1, 7), world=st.integers(1, 5), start=st.integers(0, 20))
+    def check(n, bs, world, start):
+        per_rank = [list(T.ResumableShardedSampler(n, bs, r, world, start)) for r in range(world)]
+        n_batches = max(n // (bs * world) - start, 0)
+        assert all(len(p) == n_batches == len(T.ResumableShardedSampler(n, bs, r, world, start)) for r, p in enumerate(per_rank))
+        for k in range(n_batches):
+            seen = [i for r in range(world) for i in per_rank[r][k]]
+            first = (start + k) * bs * world
+            assert seen == list(range(first, first + bs * world))
+
+    check()
