@@ -53,6 +53,17 @@ def main():
     if rank == 0:
         print(f"staged sharded inference (8-row exchange per stage), {world} strips: max rel err vs single GPU = {float(t):.2e}")
     assert float(t) < 1e-6
+    # (1c) several blocks in lock-step with one batched exchange per round (here: the same block on two different maps)
+    x2 = torch.randn(1, 48, H, W, generator=gen).to(dev)
+    with torch.no_grad():
+        full2 = blk(x2)
+        mine = shard.sharded_filtering_staged([blk, blk], [x[:, :, a:b].contiguous(), x2[:, :, a:b].contiguous()], rank, world)
+    err = max(float((mine[0] - full[:, :, a:b]).abs().max() / full.abs().max()), float((mine[1] - full2[:, :, a:b]).abs().max() / full2.abs().max()))
+    t = torch.tensor([err], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"batched staged sharded inference (two maps, one exchange per round), {world} strips: max rel err vs single GPU = {float(t):.2e}")
+    assert float(t) < 1e-6
 
     # (2) batch-sharded gradients
     xb = torch.randn(2 * world, 48, 64, 64, generator=gen).to(dev)

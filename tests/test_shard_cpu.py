@@ -222,7 +222,7 @@ def _oracle_filtering(m, coefs):
     return tuple(outs)
 
 
-def _model_worker(rank, world, port, q, img, with_blocks, cnn="torch"):
+def _model_worker(rank, world, port, q, img, with_blocks, cnn="torch", batched=True):
     _init(rank, world, port)
     m = _tiny_model()
     kernels = None
@@ -234,7 +234,13 @@ def _model_worker(rank, world, port, q, img, with_blocks, cnn="torch"):
         sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
         return shard.sharded_block_forward_staged(None, strip, rank, world, runner=EmuStageRunner(sd, blk.local_filter.n_graphs))
 
-    ex = shard.ShardedMultiScaleFilter(m, rank, world, block_forward=emu_block, cnn_kernels=kernels)
+    def emu_runner(blk):
+        return EmuStageRunner({k: v.detach().clone() for k, v in blk.state_dict().items()}, blk.local_filter.n_graphs)
+
+    if batched:     # the default form: lock-step stages, one batched exchange per round for the four scales
+        ex = shard.ShardedMultiScaleFilter(m, rank, world, stage_runner=emu_runner, cnn_kernels=kernels)
+    else:           # an independent staged exchange per block
+        ex = shard.ShardedMultiScaleFilter(m, rank, world, block_forward=emu_block, cnn_kernels=kernels)
     a, b = shard.strip_bounds(img.shape[-2], world, ex.ALIGN)[rank]
     strip = img[:, :, a:b].contiguous()
     with torch.no_grad():
@@ -244,11 +250,11 @@ def _model_worker(rank, world, port, q, img, with_blocks, cnn="torch"):
     dist.destroy_process_group()
 
 
-def _run_model(world, img, with_blocks, cnn="torch"):
+def _run_model(world, img, with_blocks, cnn="torch", batched=True):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_model_worker, args=(r, world, port, q, img, with_blocks, cnn)) for r in range(world)]
+    procs = [ctx.Process(target=_model_worker, args=(r, world, port, q, img, with_blocks, cnn, batched)) for r in range(world)]
     [p.start() for p in procs]
     res = dict(q.get(timeout=600) for _ in range(world))
     [p.join(60) for p in procs]
@@ -269,14 +275,16 @@ def test_sharded_host_cnn_equals_full_image(world, cnn):
     assert float((got - full).abs().max()) < (1e-5 if cnn == "torch" else 5e-5) * float(full.abs().max())
 
 
-def test_sharded_whole_model_equals_full_image():
-    """config 4 in miniature: the whole AbtractMultiScaleGraphFilter on two row strips - host CNN with row exchanges, the four
-    filter blocks through the per-stage halo exchange on the emulated CUDA kernels - against the module's CNN + the oracle blocks"""
-    img = torch.rand(1, 3, 256, 64, generator=torch.Generator().manual_seed(9))
+@pytest.mark.parametrize("world,batched", [(2, True), (2, False), (3, True)])
+def test_sharded_whole_model_equals_full_image(world, batched):
+    """config 4 in miniature: the whole AbtractMultiScaleGraphFilter on row strips - host CNN with row exchanges, the four
+    filter blocks through the per-stage halo exchange on the emulated CUDA kernels (batched over the scales, or one block at a
+    time) - against the module's CNN + the oracle blocks; world 3 has a first / middle / last rank"""
+    img = torch.rand(1, 3, 128 * world, 64, generator=torch.Generator().manual_seed(9))
     m = _tiny_model()
     with torch.no_grad():
         full = m.decode(_oracle_filtering(m, m.encode(img)))
-    got = _run_model(2, img, with_blocks=True)
+    got = _run_model(world, img, with_blocks=True, batched=batched)
     assert got.shape == full.shape and torch.isfinite(got).all()
     assert float((got - full).norm() / full.norm()) < 1e-5
 

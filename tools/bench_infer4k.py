@@ -6,7 +6,8 @@
 The four LocalLowpassFilteringBlock of the v13 model run (no_grad) on the feature maps of one 3840x2160 image:
 [1,48,2160,3840], [1,96,1080,1920], [1,192,540,960], [1,384,270,480].  With N ranks every map is cut into N row
 strips (boundaries at even rows) and each block does one 26-row NCCL halo exchange (shard.sharded_block_forward).
-`--staged`: one 8-row exchange per solver stage instead.  `--model`: the WHOLE v13 network (host CNN on strips with one
+`--staged`: one 8-row exchange per solver stage instead; `--batched`: the same with the four scales in lock-step and one
+batched exchange per round (shard.sharded_filtering_staged).  `--model`: the WHOLE v13 network (host CNN on strips with one
 exchanged row per 3x3 convolution + the staged filter blocks, shard.ShardedMultiScaleFilter) on the 3-channel image.
 `--torch-cnn`: with --model, keep the LocalNonLinearBlocks on the PyTorch modules instead of host_cnn.py's kernels.
 `--steps K --warmup W` (default 5 / 3).
@@ -61,6 +62,8 @@ def main():
         with torch.no_grad():
             if whole:
                 return ex(img)
+            if "--batched" in sys.argv:     # lock-step stages, one batched exchange per round for the four scales
+                return shard.sharded_filtering_staged(blocks, strips, rank, world)
             if staged:
                 return [shard.sharded_block_forward_staged(blk, x, rank, world) for blk, x in zip(blocks, strips)]
             return [shard.sharded_block_forward(blk, x, rank, world) for blk, x in zip(blocks, strips)]
@@ -89,7 +92,8 @@ def main():
                                                   "exchange per solver stage, LocalNonLinearBlocks on "
                                                   + ("the PyTorch modules" if "--torch-cnn" in sys.argv else "libglrgtv kernels + cuBLAS")) if whole else
                                      "v13 four filter blocks, forward, feature maps of one 3840x2160 image, row strips, "
-                                     + ("8-row halo exchange per solver stage" if staged else "26-row halo exchange per block")}}))
+                                     + ("8-row halo exchange per solver stage, batched over the scales" if "--batched" in sys.argv else
+                                        "8-row halo exchange per solver stage" if staged else "26-row halo exchange per block")}}))
     if world > 1:
         dist.destroy_process_group()
 
