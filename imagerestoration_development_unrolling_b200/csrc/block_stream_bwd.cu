@@ -585,11 +585,14 @@ __global__ void __launch_bounds__(BwLaunch<MODE>::MAXT, BwLaunch<MODE>::MINB) k_
         for (int i = tid; i < n4; i += NT) st4(smem + 4 * i, z4);
         __syncthreads();
     }
-    // roles in thread order: fine T | fine L | coarse T | coarse L   (L only where the stage has a GLR part)
+    // roles in thread order: fine T | fine L | coarse T | coarse L   (L only where the stage has a GLR part).  Role boundaries are
+    // whole warps; the warp index is broadcast from lane 0 so that the compiler KNOWS the role branch is warp-uniform (otherwise
+    // every shuffle inside a role is bracketed by convergence barriers)
     const int bFL = NF, bCT = HAS_L ? 2 * NF : NF, bCL = bCT + NC;
-    if (tid < bFL) bw_walk<MODE, XW, false, true>(a, smem, tid / GL, NF / GL, tid % GL, GL);
-    else if (HAS_L && tid < bCT) bw_walk<MODE, XW, true, true>(a, smem, (tid - bFL) / GL, NF / GL, (tid - bFL) % GL, GL);
-    else if (!HAS_L || tid < bCL) bw_walk<MODE, XW, false, false>(a, smem, (tid - bCT) / GLc, NC / GLc, (tid - bCT) % GLc, GL);
+    const int wtid = 32 * (int)__shfl_sync(0xffffffffu, (float)(tid >> 5), 0);
+    if (wtid < bFL) bw_walk<MODE, XW, false, true>(a, smem, tid / GL, NF / GL, tid % GL, GL);
+    else if (HAS_L && wtid < bCT) bw_walk<MODE, XW, true, true>(a, smem, (tid - bFL) / GL, NF / GL, (tid - bFL) % GL, GL);
+    else if (!HAS_L || wtid < bCL) bw_walk<MODE, XW, false, false>(a, smem, (tid - bCT) / GLc, NC / GLc, (tid - bCT) % GLc, GL);
     else bw_walk<MODE, XW, true, false>(a, smem, (tid - bCL) / GLc, NC / GLc, (tid - bCL) % GLc, GL);
 }
 
