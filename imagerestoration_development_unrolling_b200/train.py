@@ -168,13 +168,31 @@ class ResumableShardedSampler(torch.utils.data.Sampler):
             yield list(range(first, first + self.bs))
 
 
+def validate(model, dataset, device, limit: Optional[int] = None) -> float:
+    """Mean PSNR (dB, on 0..255 values after clamp + img_as_ubyte, the reference's validation loop scripts_v2:253-287) of `model`
+    over `dataset` items (noisy, clean) [H,W,3]; the model is put in eval mode and returned to its previous mode."""
+    from . import evalpipe
+    was_training = model.training
+    model.eval()
+    try:
+        n = len(dataset) if limit is None else min(limit, len(dataset))
+        noisy, clean = [], []
+        for i in range(n):
+            a, b = dataset[i]
+            noisy.append(a.permute(2, 0, 1)[None].to(device))
+            clean.append(evalpipe.to_ubyte(b.permute(2, 0, 1)[None].to(device).clamp(0.0, 1.0)))
+        return evalpipe.evaluate(model, noisy, clean)
+    finally:
+        model.train(was_training)
+
+
 # ---------------------------------------------------------------------------------------------------- the loop
 def train(conf: dict, device: Optional[torch.device] = None, on_step: Optional[Callable[[int, float], None]] = None) -> nn.Module:
     """Run (or resume) the experiment `conf` to `train.total_iters` iterations; returns the trained model."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     tc = dict(total_iters=1000, checkpoint_every=5000, log_every=100, verbose_rate=1000, num_workers=0, optimizer=None,
-              w_mse=0.1, w_stab=0.5, latent_sigma=0.05, host_cnn_kernels=False)
+              w_mse=0.1, w_stab=0.5, latent_sigma=0.05, host_cnn_kernels=False, validate_every=0)
     tc.update(conf.get("train") or {})
     if tc["host_cnn_kernels"]:        # opt-in: the host CNN's LocalNonLinearBlocks on libglrgtv as well (host_cnn.py)
         from . import deep_multiscale_GGLR_GGTV_v1x0 as v13
@@ -196,6 +214,8 @@ def train(conf: dict, device: Optional[torch.device] = None, on_step: Optional[C
     sampler = ResumableShardedSampler(len(dataset), bs, rank, world, start_batch=i)
     loader = torch.utils.data.DataLoader(dataset, batch_sampler=sampler, num_workers=tc["num_workers"])
     gen = torch.Generator(device=device)
+    vconf = conf["datasets"].get("val")
+    val_set = DATASET_TYPES[vconf.get("type", "SyntheticNoisyPatches")](**(vconf.get("dataset_args") or {})) if vconf else None
     params = [p for p in model.parameters() if p.requires_grad]
     flat = None
     for noisy, clean in loader:
@@ -213,6 +233,11 @@ def train(conf: dict, device: Optional[torch.device] = None, on_step: Optional[C
             on_step(i, float(loss.detach()))
         if rank == 0 and tc["log_every"] and i % tc["log_every"] == 0:
             LOG.info("iter=%d loss=%.6f lr=%.3e", i, float(loss.detach()), optimizer.param_groups[0]["lr"])
+        if rank == 0 and val_set is not None and tc["validate_every"] and (i + 1) % tc["validate_every"] == 0:
+            psnr = validate(model, val_set, device)                 # rank 0 only: no collective inside (scripts_v2:253-287)
+            LOG.info("FINISH VAL - iter=%d - psnr_testing=%.4f", i, psnr)
+            if on_step is not None:
+                on_step(i, {"psnr": psnr})
         if rank == 0 and ((i + 1) % tc["checkpoint_every"] == 0 or i + 1 == tc["total_iters"]):
             save_checkpoint(folder, 0, i, model, optimizer, lr_scheduler, tc["verbose_rate"])
         i += 1

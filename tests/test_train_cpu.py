@@ -150,3 +150,27 @@ def test_sampler_partition_properties():
             assert seen == list(range(first, first + bs * world))
 
     check()
+
+
+def test_validation_psnr_during_training(tmp_path):
+    """datasets.val + train.validate_every: PSNR on quantised 0..255 images as the reference's validation loop computes it"""
+    conf = _conf(tmp_path, total=4)
+    conf["datasets"]["val"] = {"type": "SyntheticNoisyPatches", "dataset_args": {"patch_size": [10, 12], "lambda_noise": 25.0, "max_num_patchs": 3, "seed": 7}}
+    conf["train"]["validate_every"] = 2
+    seen = []
+    model = T.train(conf, torch.device("cpu"), on_step=lambda i, v: seen.append((i, v)))
+    psnrs = [(i, v["psnr"]) for i, v in seen if isinstance(v, dict)]
+    assert [i for i, _ in psnrs] == [1, 3] and all(5.0 < p < 60.0 for _, p in psnrs)
+    assert model.training                                           # validation restores train mode
+    # the same number by hand for the last model state: 10x12 is padded to 16x16 (reflect), cropped back, clamped, quantised
+    ds = T.SyntheticNoisyPatches(patch_size=[10, 12], lambda_noise=25.0, max_num_patchs=3, seed=7)
+    vals = []
+    model.eval()
+    with torch.no_grad():
+        for k in range(3):
+            noisy, clean = ds[k]
+            x = torch.nn.functional.pad(noisy.permute(2, 0, 1)[None], (0, 4, 0, 6), mode="reflect")
+            out = torch.round(model(x)[:, :, :10, :12].clamp(0, 1) * 255)
+            ref = torch.round(clean.permute(2, 0, 1)[None].clamp(0, 1) * 255)
+            vals.append(20 * torch.log10(255.0 / torch.sqrt(torch.mean((ref - out) ** 2))))
+    assert abs(float(torch.stack(vals).mean()) - psnrs[-1][1]) < 1e-4
