@@ -48,3 +48,25 @@ def test_missing_library_fails_loudly(tmp_path):
     import pytest
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         L.load(str(tmp_path / "nope.so"))
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_binding(tmp_path):
+    """include/glrgtv.h compiles as strict C99 (the boundary is a C ABI, not C++), and every POD struct has the size and field
+    offsets the ctypes binding assumes - a drift between header and binding would corrupt arguments silently"""
+    pairs = [("glrgtv_shape", L.Shape), ("glrgtv_window", L.Window), ("glrgtv_stats", L.Stats), ("glrgtv_opparams", L.OpParams),
+             ("glrgtv_block_params", L.BlockParams), ("glrgtv_block_grads", L.BlockGrads), ("glrgtv_block_saved", L.BlockSaved)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "glrgtv.h"', "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{field} %zu\\n", offsetof({cname}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for field, _ in cls._fields_:
+            assert int(got[f"{cname}.{field}"]) == getattr(cls, field).offset, (cname, field)
