@@ -76,21 +76,24 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 
-def build_emu(force=False):
-    """g++ emulation build of the same kernel sources (tests only; never loaded by the package)."""
-    if not force and not _stale(EMU_LIB, _deps()):
-        return EMU_LIB
-    os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DGLRGTV_EMU", "-Wall", "-Wno-unused-function",
-           "-Wno-unknown-pragmas", "-Wno-unused-variable", "-o", EMU_LIB]
+def build_emu(force=False, asan=False):
+    """g++ emulation build of the same kernel sources (tests only; never loaded by the package).
+    asan=True: a second library built with AddressSanitizer and exact-size shared-memory blocks (tools/emu_asan.sh)."""
+    target = EMU_LIB[:-3] + "_asan.so" if asan else EMU_LIB
+    if not force and not _stale(target, _deps()):
+        return target
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    opt = ["-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=address", "-DGLRGTV_EMU_EXACT_SMEM"] if asan else ["-O2"]
+    cmd = ["g++"] + opt + ["-std=c++17", "-fPIC", "-shared", "-DGLRGTV_EMU", "-Wall", "-Wno-unused-function",
+                           "-Wno-unknown-pragmas", "-Wno-unused-variable", "-o", target]
     for src in _sources():
         cmd += ["-x", "c++", src]
     subprocess.check_call(cmd)
-    return EMU_LIB
+    return target
 
 
 if __name__ == "__main__":
     if "--emu" in sys.argv:
-        print(build_emu(force=True))
+        print(build_emu(force=True, asan="--asan" in sys.argv))
     else:
         print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))

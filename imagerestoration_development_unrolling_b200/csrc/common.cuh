@@ -62,8 +62,22 @@ static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; ret
 static inline float __ldg(const float* p) { return *p; }
 typedef void* cudaStream_t;
 #define GLR_SMEM_DECL(name) float* name = emu_smem
+// GLRGTV_EMU_EXACT_SMEM (the AddressSanitizer build, tools/emu_asan.sh): the dynamic shared memory of a launch is a heap block of
+// exactly the requested size, so a kernel that indexes past its own layout trips the sanitizer instead of landing in scratch
+#ifdef GLRGTV_EMU_EXACT_SMEM
+struct EmuSmemScope {
+    float* saved;
+    void* mine;
+    explicit EmuSmemScope(size_t bytes) : saved(emu_smem), mine(aligned_alloc(64, ((bytes ? bytes : 64) + 63) / 64 * 64)) { emu_smem = (float*)mine; }
+    ~EmuSmemScope() { emu_smem = saved; free(mine); }
+};
+#define GLR_EMU_SMEM_SCOPE(bytes) EmuSmemScope smem_scope_((size_t)(bytes))
+#else
+#define GLR_EMU_SMEM_SCOPE(bytes) ((void)0)
+#endif
 #define GLR_LAUNCH(kernel, grid, block, smem_bytes, stream, ...)                       \
     do {                                                                               \
+        GLR_EMU_SMEM_SCOPE(smem_bytes);                                                \
         emu_dim3 g_ = (grid);                                                          \
         gridDim = g_;                                                                  \
         blockDim = emu_dim3(1, 1, 1);                                                  \
@@ -78,6 +92,7 @@ typedef void* cudaStream_t;
 // launch with real per-thread semantics: blockDim.x fibers per block (kernels that use shuffles / barriers)
 #define GLR_LAUNCH_FIBERS(kernel, grid, block, smem_bytes, stream, ...)                \
     do {                                                                               \
+        GLR_EMU_SMEM_SCOPE(smem_bytes);                                                \
         emu_dim3 g_ = (grid);                                                          \
         gridDim = g_;                                                                  \
         blockDim = emu_dim3((block), 1, 1);                                            \

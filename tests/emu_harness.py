@@ -18,7 +18,7 @@ _emu = None
 def emu_lib():
     global _emu
     if _emu is None:
-        path = B.build_emu()
+        path = B.build_emu(asan=os.environ.get("GLRGTV_EMU_ASAN") == "1")     # tools/emu_asan.sh preloads libasan and sets this
         _emu = L.bind(ctypes.CDLL(path), only=[n for n in L.EXPORTED if hasattr(ctypes.CDLL(path), n)])
     return _emu
 
