@@ -13,7 +13,7 @@ set +e
 GLRGTV_EMU_ASAN=1 LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0:halt_on_error=1:detect_stack_use_after_return=0:log_path=$LOG \
     python -m pytest "$@" -x -q -p no:cacheprovider
 rc=$?
-if ls $LOG.* >/dev/null 2>&1; then          # the sanitizer aborts the interpreter: its report is in the log, not in pytest's output
+if grep -qs "ERROR: AddressSanitizer" $LOG.*; then   # the sanitizer aborts the interpreter: its report is in the log, not in pytest's output
     echo "---- AddressSanitizer report ----"; head -40 $LOG.*; [ $rc -eq 0 ] && rc=1
 fi
 exit $rc
