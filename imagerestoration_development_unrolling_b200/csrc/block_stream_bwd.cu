@@ -482,6 +482,7 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
                     const float* xs = xring + (((m + 1) & 1) * NK * 2) * Wp + lcol;
                     const float* cs = cring + (((r >> 1) & 3) * NK * 2) * Wpc + (lcol >> 1);
                     Row V = row_ld(xs), Fw = row_ld(xs + Wp);
+                    GLR_CHECK_ALIGN(cs, 8);
                     float2 cV = *reinterpret_cast<const float2*>(cs), cF = *reinterpret_cast<const float2*>(cs + Wpc);
                     if (HAS_L) {
                         const Row VL = row_ld(xs + 2 * Wp), FL = row_ld(xs + 3 * Wp);

@@ -547,6 +547,7 @@ __device__ __forceinline__ void stream_walk(const StreamFwdArgs& a, float* smem,
                         }
                     } else {
                         const float* slot = cring + ((r >> 1) & 1) * NRING * Wpc + (lcol >> 1);
+                        GLR_CHECK_ALIGN(slot, 8);
                         const float2 cz = *reinterpret_cast<const float2*>(slot);
                         const Row zq = row_ld(zring + zqs * Wp + lcol);      // row t-3 is still in the ring
 #pragma unroll

@@ -62,6 +62,19 @@ static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; ret
 static inline float __ldg(const float* p) { return *p; }
 typedef void* cudaStream_t;
 #define GLR_SMEM_DECL(name) float* name = emu_smem
+// alignment of vector accesses and async copies: a misaligned 16-byte access is a fault on the GPU and silent on the CPU
+#ifdef GLRGTV_EMU_EXACT_SMEM
+#include <cstdio>
+#define GLR_CHECK_ALIGN(p, n)                                                                              \
+    do {                                                                                                   \
+        if (((uintptr_t)(p)) & ((n) - 1)) {                                                                \
+            fprintf(stderr, "glrgtv emu: %d-byte access to misaligned address %p at %s:%d\n", (int)(n), (const void*)(p), __FILE__, __LINE__); \
+            abort();                                                                                       \
+        }                                                                                                  \
+    } while (0)
+#else
+#define GLR_CHECK_ALIGN(p, n) ((void)0)
+#endif
 // GLRGTV_EMU_EXACT_SMEM (the AddressSanitizer build, tools/emu_asan.sh): the dynamic shared memory of a launch is a heap block of
 // exactly the requested size, so a kernel that indexes past its own layout trips the sanitizer instead of landing in scratch
 #ifdef GLRGTV_EMU_EXACT_SMEM
@@ -111,6 +124,7 @@ static inline int glr_memset_async(void* p, int v, size_t n, cudaStream_t) { mem
 #else
 // ------------------------------------------------------------------ CUDA build
 #include <cuda_runtime.h>
+#define GLR_CHECK_ALIGN(p, n) ((void)0)
 #define GLR_SMEM_DECL(name) extern __shared__ __align__(16) float name[]
 extern unsigned long long g_glr_launches;  // kernels launched by this library (bench.py reports it)
 #define GLR_LAUNCH(kernel, grid, block, smem_bytes, stream, ...) \

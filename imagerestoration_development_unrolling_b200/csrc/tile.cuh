@@ -89,10 +89,12 @@ __device__ __forceinline__ WPl<G, R> wplanes_at(float* smem, int off) {
 }
 
 __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+    GLR_CHECK_ALIGN(p, 16);
     float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 __device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+    GLR_CHECK_ALIGN(p, 16);
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
 static inline int glr_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
@@ -296,7 +298,10 @@ struct Raw {
     static constexpr int ROWS = GF::TR + 12, P = GF::TC + 16, NQ = P / 4, FLOATS = ROWS * P;
 };
 #ifdef GLRGTV_EMU
-__device__ __forceinline__ void cp_async16(float* dst, const float* src) { for (int j = 0; j < 4; ++j) dst[j] = src[j]; }
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    GLR_CHECK_ALIGN(dst, 16); GLR_CHECK_ALIGN(src, 16);
+    for (int j = 0; j < 4; ++j) dst[j] = src[j];
+}
 __device__ __forceinline__ void cp_async4(float* dst, const float* src) { *dst = *src; }
 __device__ __forceinline__ void cp_async_commit() {}
 __device__ __forceinline__ void cp_async_wait_all() {}
