@@ -68,8 +68,22 @@ void emu_run_block(unsigned nthreads, void (*fn)(void*), void* arg) {
     }
     emu_fiber_mode = true;
     unsigned remaining = nthreads;
+    // GLRGTV_EMU_SCHED = reverse | random[:seed]: the order in which the fibers of a block run between two synchronisation points.
+    // A kernel whose shared-memory hand-overs are all separated by a barrier (or a warp shuffle) gives the same result under every
+    // order; one that relies on "the lower thread ran first" does not - a race detector for the barrier discipline (tools/emu_races.sh)
+    const char* sched = getenv("GLRGTV_EMU_SCHED");
+    const int mode = !sched ? 0 : !strncmp(sched, "reverse", 7) ? 1 : !strncmp(sched, "random", 6) ? 2 : 0;
+    unsigned long long lcg = 0x9E3779B97F4A7C15ull ^ (mode == 2 && sched[6] == ':' ? strtoull(sched + 7, nullptr, 10) : 0ull);
+    std::vector<unsigned> order(nthreads);
+    for (unsigned i = 0; i < nthreads; ++i) order[i] = mode == 1 ? nthreads - 1 - i : i;
     while (remaining) {
-        for (unsigned i = 0; i < nthreads; ++i) {
+        if (mode == 2)
+            for (unsigned i = nthreads; i > 1; --i) {                // a fresh permutation for every sweep
+                lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[i - 1], order[(unsigned)((lcg >> 33) % i)]);
+            }
+        for (unsigned k = 0; k < nthreads; ++k) {
+            const unsigned i = order[k];
             if (rt.done[i]) continue;
             rt.cur = i;
             threadIdx = emu_dim3(i, 0, 0);
