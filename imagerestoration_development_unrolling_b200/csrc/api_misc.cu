@@ -32,6 +32,53 @@ void fiber_main() {
     swapcontext(&rt.ctx[rt.cur], &rt.sched);
 }
 }  // namespace
+// ---- late-completing asynchronous copies (GLRGTV_EMU_ASYNC=late), see common.cuh ----
+bool emu_async_late = false;
+namespace {
+struct PendingCopy { float* dst; const float* src; int n; unsigned group; };
+struct PendingBulk { float* dst; const float* src; unsigned bytes; const void* bar; };
+struct AsyncRt {
+    std::vector<std::vector<PendingCopy>> q;      // per CUDA thread of the block
+    std::vector<unsigned> open_group;             // id of the group the thread's next copies belong to (= groups committed so far)
+    std::vector<PendingBulk> bulk;                // per block
+};
+thread_local AsyncRt art;
+unsigned async_slot() { return emu_fiber_mode ? rt.cur : 0u; }
+void async_reset(unsigned nthreads) {
+    const char* e = getenv("GLRGTV_EMU_ASYNC");
+    emu_async_late = e && !strcmp(e, "late");
+    art.q.assign(nthreads ? nthreads : 1, {});
+    art.open_group.assign(nthreads ? nthreads : 1, 0u);
+    art.bulk.clear();
+}
+}  // namespace
+void emu_async_reset_for_launch() { async_reset(1); }
+void emu_async_push(float* dst, const float* src, int n) {
+    const unsigned t = async_slot();
+    art.q[t].push_back({dst, src, n, art.open_group[t]});
+}
+void emu_async_commit() { ++art.open_group[async_slot()]; }
+void emu_async_wait(int keep) {
+    const unsigned t = async_slot();
+    const unsigned committed = art.open_group[t];                      // groups 0 .. committed-1 are closed
+    const unsigned done_below = committed > (unsigned)keep ? committed - (unsigned)keep : 0u;
+    auto& q = art.q[t];
+    size_t w = 0;
+    for (size_t i = 0; i < q.size(); ++i) {
+        if (q[i].group < done_below) { for (int j = 0; j < q[i].n; ++j) q[i].dst[j] = q[i].src[j]; }
+        else q[w++] = q[i];
+    }
+    q.resize(w);
+}
+void emu_bulk_push(float* dst, const float* src, unsigned bytes, const void* bar) { art.bulk.push_back({dst, src, bytes, bar}); }
+void emu_bulk_wait(const void* bar) {
+    size_t w = 0;
+    for (size_t i = 0; i < art.bulk.size(); ++i) {
+        if (art.bulk[i].bar == bar) memcpy(art.bulk[i].dst, art.bulk[i].src, art.bulk[i].bytes);
+        else art.bulk[w++] = art.bulk[i];
+    }
+    art.bulk.resize(w);
+}
 void emu_barrier() {
     const unsigned g = rt.bar_gen;
     if (++rt.bar_count >= rt.alive) { rt.bar_count = 0; ++rt.bar_gen; return; }
@@ -50,6 +97,7 @@ float emu_shfl(float v, int src_lane) {
 void emu_run_block(unsigned nthreads, void (*fn)(void*), void* arg) {
     rt.n = nthreads; rt.alive = nthreads; rt.fn = fn; rt.arg = arg;
     rt.bar_count = 0; rt.bar_gen = 0;
+    async_reset(nthreads);
     if (rt.ctx.size() < nthreads) {
         const size_t old = rt.ctx.size();
         rt.ctx.resize(nthreads);

@@ -40,6 +40,17 @@ extern thread_local bool emu_fiber_mode;
 void emu_barrier();
 float emu_shfl(float v, int src_lane);   // value of `v` held by lane `src_lane` of the caller's warp
 void emu_run_block(unsigned nthreads, void (*fn)(void*), void* arg);
+// Asynchronous copies (cp.async / cp.async.bulk) complete at ISSUE time by default - the earliest legal moment, the worst case for
+// write-after-read hazards.  With GLRGTV_EMU_ASYNC=late they complete at the LATEST legal moment instead: a cp.async lands when its
+// thread executes the wait_group that covers it, a bulk copy when some thread first waits on its mbarrier - the worst case for
+// read-before-arrival hazards (a missing or too-shallow wait).  A correct kernel gives the same result in both modes.
+extern bool emu_async_late;
+void emu_async_push(float* dst, const float* src, int nfloats);
+void emu_async_commit();
+void emu_async_wait(int keep_groups);           // complete all but the `keep_groups` most recent commit groups of this thread
+void emu_bulk_push(float* dst, const float* src, unsigned bytes, const void* bar);
+void emu_bulk_wait(const void* bar);
+void emu_async_reset_for_launch();
 static inline void __syncthreads() { if (emu_fiber_mode) emu_barrier(); }
 static inline float __shfl_sync(unsigned, float v, int src, int width = 32) {
     const int lane = (int)(threadIdx.x & 31u);
@@ -91,6 +102,7 @@ struct EmuSmemScope {
 #define GLR_LAUNCH(kernel, grid, block, smem_bytes, stream, ...)                       \
     do {                                                                               \
         GLR_EMU_SMEM_SCOPE(smem_bytes);                                                \
+        emu_async_reset_for_launch();                                                  \
         emu_dim3 g_ = (grid);                                                          \
         gridDim = g_;                                                                  \
         blockDim = emu_dim3(1, 1, 1);                                                  \

@@ -151,14 +151,16 @@ __device__ __forceinline__ smem_addr_t smem_addr(float* p) { return p; }
 __device__ __forceinline__ void mbar_init(smem_addr_t, unsigned) {}
 __device__ __forceinline__ void mbar_fence_init() {}
 __device__ __forceinline__ void mbar_expect_tx(smem_addr_t, unsigned) {}
-__device__ __forceinline__ void bulk_g2s(smem_addr_t dst, const float* src, unsigned bytes, smem_addr_t) {
+__device__ __forceinline__ void bulk_g2s(smem_addr_t dst, const float* src, unsigned bytes, smem_addr_t bar_) {
     GLR_CHECK_ALIGN(dst, 16); GLR_CHECK_ALIGN(src, 16); GLR_CHECK_ALIGN((uintptr_t)bytes, 16);       // cp.async.bulk: 16-byte addresses and size
+    if (emu_async_late) { emu_bulk_push(dst, src, bytes, bar_); return; }
     memcpy(dst, src, bytes);
 }
-__device__ __forceinline__ void mbar_wait(smem_addr_t, unsigned) {}
+__device__ __forceinline__ void mbar_wait(smem_addr_t bar, unsigned) { if (emu_async_late) emu_bulk_wait(bar); }
 __device__ __forceinline__ smem_addr_t smem_advance(smem_addr_t a, int floats) { return a + floats; }
 __device__ __forceinline__ void cp_async16_s(smem_addr_t dst, const float* src) {
     GLR_CHECK_ALIGN(dst, 16); GLR_CHECK_ALIGN(src, 16);
+    if (emu_async_late) { emu_async_push(dst, src, 4); return; }
     for (int j = 0; j < 4; ++j) dst[j] = src[j];
 }
 #else

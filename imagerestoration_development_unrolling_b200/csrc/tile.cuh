@@ -300,12 +300,16 @@ struct Raw {
 #ifdef GLRGTV_EMU
 __device__ __forceinline__ void cp_async16(float* dst, const float* src) {
     GLR_CHECK_ALIGN(dst, 16); GLR_CHECK_ALIGN(src, 16);
+    if (emu_async_late) { emu_async_push(dst, src, 4); return; }
     for (int j = 0; j < 4; ++j) dst[j] = src[j];
 }
-__device__ __forceinline__ void cp_async4(float* dst, const float* src) { *dst = *src; }
-__device__ __forceinline__ void cp_async_commit() {}
-__device__ __forceinline__ void cp_async_wait_all() {}
-template <int N> __device__ __forceinline__ void cp_async_wait_pending() {}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    if (emu_async_late) { emu_async_push(dst, src, 1); return; }
+    *dst = *src;
+}
+__device__ __forceinline__ void cp_async_commit() { if (emu_async_late) emu_async_commit(); }
+__device__ __forceinline__ void cp_async_wait_all() { if (emu_async_late) emu_async_wait(0); }
+template <int N> __device__ __forceinline__ void cp_async_wait_pending() { if (emu_async_late) emu_async_wait(N); }
 #else
 __device__ __forceinline__ void cp_async16(float* dst, const float* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));

@@ -12,3 +12,9 @@ for sched in reverse random:1 random:2 random:3; do
     echo "== GLRGTV_EMU_SCHED=$sched"
     GLRGTV_EMU_SCHED=$sched python -m pytest "$@" -x -q -p no:cacheprovider | tail -1
 done
+# asynchronous copies completing at the LATEST legal moment (at the covering wait_group / the first mbarrier wait) instead of at issue:
+# catches a missing or too-shallow wait, which the default mode (earliest completion: catches write-after-read hazards) cannot see
+for sched in forward reverse random:4; do
+    echo "== GLRGTV_EMU_ASYNC=late GLRGTV_EMU_SCHED=$sched"
+    GLRGTV_EMU_ASYNC=late GLRGTV_EMU_SCHED=$sched python -m pytest "$@" tests/test_emu_block.py -x -q -p no:cacheprovider | tail -1
+done
