@@ -92,7 +92,10 @@ typedef void* cudaStream_t;
 struct EmuSmemScope {
     float* saved;
     void* mine;
-    explicit EmuSmemScope(size_t bytes) : saved(emu_smem), mine(aligned_alloc(64, ((bytes ? bytes : 64) + 63) / 64 * 64)) { emu_smem = (float*)mine; }
+    explicit EmuSmemScope(size_t bytes) : saved(emu_smem), mine(aligned_alloc(64, ((bytes ? bytes : 64) + 63) / 64 * 64)) {
+        memset(mine, 0xFF, ((bytes ? bytes : 64) + 63) / 64 * 64);      // shared memory starts as garbage on the GPU: NaN bit patterns here
+        emu_smem = (float*)mine;
+    }
     ~EmuSmemScope() { emu_smem = saved; free(mine); }
 };
 #define GLR_EMU_SMEM_SCOPE(bytes) EmuSmemScope smem_scope_((size_t)(bytes))
