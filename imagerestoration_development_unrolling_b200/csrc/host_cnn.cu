@@ -15,27 +15,33 @@
 // (`top` / `bot`, [B, 2Hd, W]); NULL means the true image border (replicate).
 #include "tile.cuh"
 
-// one item = 4 consecutive pixels of one (image, sub-net): Welford over the sub-net's channels (the reference's
-// torch.var is two-pass; a sum / sum-of-squares form would cancel for features with a large mean)
+// one item = 4 consecutive pixels of one (image, sub-net).  Two passes over the sub-net's channels, as torch.var does: the mean first,
+// then the squared deviations from it (an error of the rounded mean enters the sum only to second order; a one-pass Welford update
+// is first-order sensitive to it and loses 1e-5 when the spread is small against the mean; a sum / sum-of-squares form cancels).
+// The second pass re-reads x from L1 / L2.
 __global__ void __launch_bounds__(256) k_pixel_rstd(const float* __restrict__ x, float* __restrict__ rs, int B, int nsub, int c,
                                                     long HW, float eps) {
     const long Q = HW / 4, total = (long)B * nsub * Q;
+    const float invc = 1.f / (float)c, invn = 1.f / (float)(c - 1);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long q = i % Q, bs = i / Q;
         const float* p = x + bs * c * HW + 4 * q;
-        float mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+        float mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f}, v0[4];
+        ld4(p, v0);
+        for (int k = 1; k < c; ++k) {                 // mean = x_0 + mean(x - x_0): the differences are small, so their sum rounds little
+            float v[4];
+            ld4(p + (long)k * HW, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mean[j] += v[j] - v0[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mean[j] = v0[j] + mean[j] * invc;
         for (int k = 0; k < c; ++k) {
             float v[4];
             ld4(p + (long)k * HW, v);
-            const float inv = 1.f / (float)(k + 1);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float d = v[j] - mean[j];
-                mean[j] += d * inv;
-                m2[j] += d * (v[j] - mean[j]);
-            }
+            for (int j = 0; j < 4; ++j) { const float d = v[j] - mean[j]; m2[j] += d * d; }
         }
-        const float invn = 1.f / (float)(c - 1);
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = 1.f / sqrtf(m2[j] * invn + eps);
