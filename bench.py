@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 DIMS, NGRAPHS = [48, 96, 192, 384], [8, 16, 16, 32]
 BATCH, RES = 32, 256
+GPU_BASELINE_BATCH = 8          # reference autograd keeps ~150x the activation size per block: 8 x 256^2 is what runs quickly
 METRIC, UNIT = "train_Mpix_per_s", "Mpix/s"
 WORKLOAD = ("v13 four LocalLowpassFilteringBlock fwd+bwd on feature maps of a 32x3x256x256 batch "
             "([32,48,256,256],[32,96,128,128],[32,192,64,64],[32,384,32,32])")
@@ -42,66 +43,87 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="per-rank batch (default = the config's 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_blocks_state(seed=0):
-    """default-init state dicts of the four blocks, built WITHOUT the product package's kernels
-    (module construction is plain torch)."""
-    import torch
-    from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
-    torch.manual_seed(seed)
-    return [{k: v.detach().clone() for k, v in M.LocalLowpassFilteringBlock(d, 1, g).state_dict().items()}
-            for d, g in zip(DIMS, NGRAPHS)]
-
-
-def cpu_port_step(states, xs, gs):
-    """one fwd+bwd of the four blocks with the oracle port (torch CPU, all threads)."""
-    from oracle import glr_gtv_oracle as O
-    for sd, x, g in zip(states, xs, gs):
-        O.lowpass_block_fwd_bwd(sd, x, g)
-
-
-def cpu_sample(batch, seed=1):
-    import torch
-    gen = torch.Generator().manual_seed(seed)
-    xs = [torch.randn(batch, d, RES >> s, RES >> s, generator=gen) for s, d in enumerate(DIMS)]
-    gs = [torch.randn(batch, d, RES >> s, RES >> s, generator=gen) for s, d in enumerate(DIMS)]
-    return xs, gs
-
-
 def run_cpu(steps, warmup, sample_batch=1):
+    """forward+backward of the four blocks on the host cores: the UNMODIFIED reference module (oracle/_ref, vendored by
+    oracle/vendor_ref.sh; kind "reference") when it travelled with the snapshot, else the oracle port (kind "port")."""
+    from oracle import ref_runner as R
+    if R.available():
+        mpix, dt, cores = R.time_cpu(sample_batch, RES, steps, warmup)
+        return mpix, dt, cores, "reference"
     import torch
+    from oracle import glr_gtv_oracle as O
+    from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    states = cpu_blocks_state()
-    xs, gs = cpu_sample(sample_batch)
+    torch.manual_seed(0)
+    states = [{k: v.detach().clone() for k, v in M.LocalLowpassFilteringBlock(d, 1, g).state_dict().items()} for d, g in zip(DIMS, NGRAPHS)]
+    xs, gs = R.make_inputs(sample_batch, RES, torch.device("cpu"))
+
+    def port_step():
+        for sd, x, g in zip(states, xs, gs):
+            O.lowpass_block_fwd_bwd(sd, x, g)
+
     for _ in range(warmup):
-        cpu_port_step(states, xs, gs)
+        port_step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_port_step(states, xs, gs)
+        port_step()
     dt = (time.perf_counter() - t0) / steps
-    mpix = sample_batch * RES * RES / dt / 1e6
-    return mpix, dt, cores
+    return sample_batch * RES * RES / dt / 1e6, dt, cores, "port"
+
+
+def cpu_sample_text(kind, cores, reps):
+    what = ("the reference's own deep_multiscale_GGLR_GGTV_v1x0.LocalLowpassFilteringBlock (oracle/_ref, unmodified), eager"
+            if kind == "reference" else "oracle port (oracle/glr_gtv_oracle.py)")
+    return (f"batch 1 of the {BATCH} (65,536 px per step), forward+backward of the four blocks, {what}, torch CPU fp32, "
+            f"{cores} threads, {reps} timed repetitions")
 
 
 def reference_arm(a):
-    """`--impl reference`: the reference is pure Python/PyTorch and /root/reference does not exist on the GPU box,
-    so the oracle PORT (same ATen arithmetic, oracle/glr_gtv_oracle.py) is timed on the host cores."""
+    """`--impl reference`: the reference's own implementation of the path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mpix, dt, cores = run_cpu(a.steps, a.warmup)
-    sample = f"batch 1 of the {BATCH} (65,536 px per step), forward+backward of the four blocks, torch CPU {cores} threads"
+    mpix, dt, cores, kind = run_cpu(a.steps, a.warmup)
+    sample = cpu_sample_text(kind, cores, a.steps)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def gpu_baseline(local, budget_s=170.0):
+    """The reference module itself on the same B200 (SURVEY 8d "GPU baseline"): eager and nn.Module.compile() (as
+    scripts_v2/run_abtract_lightformer_GGTV_GGLR_sigma25.py:130 runs it), TF32 as shipped (:23) and off, forward+backward of the
+    four blocks.  One subprocess per variant (its own CUDA context, a hard time limit); runs after the timed regions."""
+    from oracle import ref_runner as R
+    if not R.available():
+        return {"unavailable": "oracle/_ref not shipped"}
+    out, t_start = {}, time.perf_counter()
+    for name, mode, tf32, limit in (("eager", "eager", 1, 60), ("eager_tf32_off", "eager", 0, 60), ("compile", "compile", 1, 150)):
+        left = budget_s - (time.perf_counter() - t_start)
+        if left < 20:
+            out[name] = {"skipped": "time budget of the default bench run"}
+            continue
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "--device", "cuda", "--mode", mode, "--tf32", str(tf32),
+               "--batch", str(GPU_BASELINE_BATCH), "--res", str(RES), "--reps", "3", "--warmup", "3", "--gpu", str(local)]
+        try:
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=min(limit, left))
+            lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+            out[name] = json.loads(lines[-1]) if lines else {"failed": (p.stderr or "no output").strip()[-300:]}
+        except subprocess.TimeoutExpired:
+            out[name] = {"failed": f"no result within {int(min(limit, left))} s (graph breaks at the reference's ~820 .item() calls per block)"}
+    out["note"] = (f"reference LocalLowpassFilteringBlock x4, forward+backward, batch {GPU_BASELINE_BATCH} x {RES}x{RES}, CUDA events, "
+                   "3 warm-ups + 3 repetitions")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -360,10 +382,10 @@ def main():
             "roofline": roofline,
         }
         if world == 1 and not a.no_cpu_baseline:
-            mpix, dt, cores = run_cpu(steps=2, warmup=1)
-            line["cpu_baseline"] = {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "batch 1 of the 32 (65,536 px), fwd+bwd of the four blocks, 1 warm-up + 2 reps, "
-                                              f"oracle port on torch CPU with {cores} threads"}
+            mpix, dt, cores, kind = run_cpu(steps=3, warmup=1)
+            line["cpu_baseline"] = {"value": mpix, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_text(kind, cores, 3)}
+        if world == 1 and not a.no_gpu_baseline:
+            line["gpu_baseline"] = gpu_baseline(local)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

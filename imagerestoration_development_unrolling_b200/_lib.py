@@ -98,7 +98,8 @@ _SIGS = {
     "glrgtv_mixture_bwd": (C.c_int, [_P(Shape), fp, fp, fp, fp, fp, fp]),
     "glrgtv_pool2_fwd": (C.c_int, [_P(Shape), fp, fp, fp]),
     "glrgtv_unpool2_fwd": (C.c_int, [_P(Shape), fp, fp, fp]),
-    "glrgtv_proj_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]),
+    "glrgtv_proj_gemm_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "glrgtv_proj_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, C.c_size_t, fp]),
     "glrgtv_space_to_depth": (C.c_int, [C.c_int, C.c_long, C.c_int, C.c_int, fp, fp, fp]),
     "glrgtv_pixel_rstd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, fp, fp, fp]),
     "glrgtv_dwconv_gate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp, fp]),

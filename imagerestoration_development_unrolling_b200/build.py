@@ -24,18 +24,6 @@ NVCC_FLAGS = [
 ]
 
 
-def cutlass_include():
-    """CUTLASS / CuTe header tree vendored in this image (templates only; instantiated in csrc/proj_gemm.cu)."""
-    import importlib.util
-    for pkg, sub in (("flashinfer", "data/cutlass/include"), ("tilelang", "3rdparty/cutlass/include")):
-        spec = importlib.util.find_spec(pkg)
-        if spec and spec.submodule_search_locations:
-            d = os.path.join(list(spec.submodule_search_locations)[0], sub)
-            if os.path.exists(os.path.join(d, "cutlass", "cutlass.h")):
-                return d
-    raise RuntimeError("CUTLASS headers not found (looked in the flashinfer and tilelang packages)")
-
-
 def _sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
@@ -64,7 +52,7 @@ def build_cuda(force=False, verbose=False):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + ["-I" + cutlass_include()] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

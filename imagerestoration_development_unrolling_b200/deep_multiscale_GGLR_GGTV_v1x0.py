@@ -36,8 +36,6 @@ def _edges_of(mask: np.ndarray):
     return [d for d, on in zip(itertools.product(offs, offs), mask.reshape(-1)) if on == 1]
 
 
-PROJ_TENSOR_CORES = False      # see MixtureGTVGLR._projections
-
 class _GraphOperatorBase(nn.Module):
     """State shared by GLRFast and GTVFast (V1X0:14-125, 243-356): the window, four per-channel
     stats_kernel_p* parameters and multiM."""
@@ -169,20 +167,17 @@ class MixtureGTVGLR(nn.Module):
 
     def _projections(self, patchs):
         """patchs_features_extraction00 / 01 (V1X0:556-612, 712, 725) as plain GEMMs on the Conv2d weights: a 1x1 conv is
-        W[2C,C] @ x[C,HW]; the 2x2 stride-2 conv is the same after a space-to-depth.  cuBLAS serves these far better than
-        cuDNN's fp32 convolution fallbacks; the parameters stay the reference's Conv2d's."""
+        W[2C,C] @ x[C,HW]; the 2x2 stride-2 conv is the same after a space-to-depth.  The parameters stay the reference's Conv2d's."""
         b, c, h, w = patchs.shape
         w00 = self.patchs_features_extraction00[0].weight.reshape(2 * c, c)
         w01a = self.patchs_features_extraction01[0].weight.reshape(c, 4 * c)
         w01b = self.patchs_features_extraction01[1].weight.reshape(2 * c, c)
-        # cuBLAS fp32 (SIMT) batched GEMM by default.  ops.proj_gemm (3xTF32 on the tensor cores through mma.sync, fp32-level
-        # accuracy, csrc/proj_gemm.cu) is available behind PROJ_TENSOR_CORES but MEASURED SLOWER on B200 (tools/proj_times.py:
-        # 0.93 vs 0.63 ms for the scale-0 forward GEMM): legacy mma.sync TF32 runs far below tcgen05 rates and 3x of it loses to
-        # the fp32 pipe.  A tcgen05 kind::tf32 kernel is what would pay here (DESIGN.md, next).
-        if PROJ_TENSOR_CORES and (h * w) % 16 == 0 and c % 4 == 0:
-            mm = lambda wm, x3: ops.proj_gemm(wm, x3, False)
-        else:
-            mm = ops.projection                       # cuBLAS fp32 forward / input gradient, split-reduction weight gradient
+        # all projection GEMMs (forward, input and weight gradients) run on the tcgen05 tensor cores with the three-pass TF32
+        # split (csrc/proj_tc.cu): fp32-level accuracy, so the 1e-4 parity bar holds without an fp32 SIMT library GEMM
+        def mm(wm, x3):
+            if ops.proj_supported(wm.shape[0], wm.shape[1], x3.shape[2]):
+                return ops.projection(wm, x3)
+            return torch.matmul(wm, x3)              # extents that are not multiples of 4 (no 16-byte TMA rows): library GEMM
         feat0 = mm(w00, patchs.reshape(b, c, h * w)).reshape(b, 2 * c, h, w)
         s2d = ops.space_to_depth(patchs, False) if w % 8 == 0 else nn.functional.pixel_unshuffle(patchs, 2)
         xs = s2d.reshape(b, 4 * c, (h // 2) * (w // 2))

@@ -391,7 +391,12 @@ def _gn_setup(ctx, inputs, output):
 gather_neighbors.register_autograd(lambda ctx, g: (gather_neighbors_bwd(g, ctx.edges), None), setup_context=_gn_setup)
 
 
-# ====================================================================== feature projections (tensor-core 3xTF32 GEMMs)
+# ====================================================================== feature projections (tcgen05 3xTF32 GEMMs, csrc/proj_tc.cu)
+def proj_supported(M: int, K: int, N: int) -> bool:
+    """shapes glrgtv_proj_gemm / glrgtv_proj_wgrad take: every extent a multiple of 4 (16-byte TMA strides)"""
+    return M % 4 == 0 and K % 4 == 0 and N % 4 == 0
+
+
 @torch.library.custom_op(f"{_NS}::proj_gemm", mutates_args=())
 def proj_gemm(w: Tensor, x: Tensor, transpose_w: bool) -> Tensor:
     """w [M,K], x [B,K,N] -> [B,M,N] = w @ x   (transpose_w: x [B,M,N] -> [B,K,N] = w^T @ x); glrgtv_proj_gemm"""
@@ -402,7 +407,8 @@ def proj_gemm(w: Tensor, x: Tensor, transpose_w: bool) -> Tensor:
     if R != (M if transpose_w else K):
         raise RuntimeError(f"proj_gemm: weight {tuple(w.shape)} does not match input {tuple(x.shape)}")
     y = x.new_empty(B, K if transpose_w else M, N)
-    _call("glrgtv_proj_gemm", x, int(bool(transpose_w)), B, M, N, K, w, x, y)
+    ws = x.new_empty(2 * M * K)
+    _call("glrgtv_proj_gemm", x, int(bool(transpose_w)), B, M, N, K, w, x, y, ws, ws.numel() * 4)
     return y
 
 
@@ -410,6 +416,23 @@ def proj_gemm(w: Tensor, x: Tensor, transpose_w: bool) -> Tensor:
 def _(w, x, transpose_w):
     M, K = w.shape
     return x.new_empty(x.shape[0], K if transpose_w else M, x.shape[2])
+
+
+@torch.library.custom_op(f"{_NS}::proj_wgrad", mutates_args=())
+def proj_wgrad(gy: Tensor, x: Tensor) -> Tensor:
+    """gy [B,M,N], x [B,K,N] -> gw [M,K] = sum_b gy[b] @ x[b]^T   (glrgtv_proj_wgrad)"""
+    _chk(gy, x)
+    gy, x = _c(gy), _c(x)
+    B, M, N = gy.shape
+    K = x.shape[1]
+    gw = gy.new_zeros(M, K)
+    _call("glrgtv_proj_wgrad", gy, B, M, N, K, gy, x, gw)
+    return gw
+
+
+@proj_wgrad.register_fake
+def _(gy, x):
+    return gy.new_empty(gy.shape[1], x.shape[1])
 
 
 def _pg_setup(ctx, inputs, output):
@@ -421,13 +444,19 @@ def _pg_setup(ctx, inputs, output):
 def _pg_backward(ctx, gy):
     w, x = ctx.saved_tensors
     gy = _c(gy)
-    gx = proj_gemm(w, gy, not ctx.transpose_w)
-    # weight gradient: one reduction over batch and pixels - cuBLAS (split-K), [M,K] = sum_b gy[b] x[b]^T (or its transpose)
-    gw = (torch.bmm(x, gy.transpose(1, 2)) if ctx.transpose_w else torch.bmm(gy, x.transpose(1, 2))).sum(0)
+    gx = proj_gemm(w, gy, not ctx.transpose_w) if ctx.needs_input_grad[1] else None
+    gw = None
+    if ctx.needs_input_grad[0]:
+        gw = proj_wgrad(x, gy) if ctx.transpose_w else proj_wgrad(gy, x)
     return gw, gx, None
 
 
 proj_gemm.register_autograd(_pg_backward, setup_context=_pg_setup)
+
+
+def projection(w: Tensor, x: Tensor) -> Tensor:
+    """y[b] = w @ x[b] with gradients, all three GEMMs on the tensor cores"""
+    return proj_gemm(w, x, False)
 
 
 # ---- host CNN, inference forward: the memory-bound pieces of LocalNonLinearBlock (host_cnn.py)
@@ -502,57 +531,6 @@ def _s2d_setup(ctx, inputs, output):
 
 
 space_to_depth.register_autograd(lambda ctx, g: (space_to_depth(g, not ctx.inverse), None), setup_context=_s2d_setup)
-
-
-# ---- projection with a library forward / input gradient and the split-reduction weight-gradient kernel
-def proj_wgrad_supported(M: int, K: int, N: int) -> bool:
-    return N % 32 == 0 and ((M % 96 == 0 and K % 48 == 0) or (K % 96 == 0 and M % 48 == 0))
-
-
-@torch.library.custom_op(f"{_NS}::proj_wgrad", mutates_args=())
-def proj_wgrad(gy: Tensor, x: Tensor) -> Tensor:
-    """gy [B,M,N], x [B,K,N] -> gw [M,K] = sum_b gy[b] @ x[b]^T   (glrgtv_proj_wgrad)"""
-    _chk(gy, x)
-    gy, x = _c(gy), _c(x)
-    B, M, N = gy.shape
-    K = x.shape[1]
-    gw = gy.new_zeros(M, K)
-    _call("glrgtv_proj_wgrad", gy, B, M, N, K, gy, x, gw)
-    return gw
-
-
-@proj_wgrad.register_fake
-def _(gy, x):
-    return gy.new_empty(gy.shape[1], x.shape[1])
-
-
-class _Projection(torch.autograd.Function):
-    """y[b] = w @ x[b]: cuBLAS fp32 for y and gx, csrc/proj_wgrad.cu for gw (cuBLAS' batched GEMM + sum leaves most of the
-    GPU idle on this tiny-output, long-reduction shape)."""
-
-    @staticmethod
-    def forward(ctx, w, x):
-        ctx.save_for_backward(w, x)
-        return torch.bmm(w.unsqueeze(0).expand(x.shape[0], -1, -1), x)
-
-    @staticmethod
-    def backward(ctx, gy):
-        w, x = ctx.saved_tensors
-        gy = _c(gy)
-        gx = torch.bmm(w.t().unsqueeze(0).expand(x.shape[0], -1, -1), gy) if ctx.needs_input_grad[1] else None
-        gw = None
-        if ctx.needs_input_grad[0]:
-            # measured on B200 (tools/proj_times.py): the split-reduction kernel runs at ~31 TFLOP/s whatever the shape; cuBLAS
-            # beats that once the output tile grid is large enough to fill the GPU (M*K above ~10K), and loses 2.7x below
-            if proj_wgrad_supported(w.shape[0], w.shape[1], x.shape[2]) and w.shape[0] * w.shape[1] <= 9216:
-                gw = proj_wgrad(gy, x)
-            else:
-                gw = torch.bmm(gy, x.transpose(1, 2)).sum(0)
-        return gw, gx
-
-
-def projection(w: Tensor, x: Tensor) -> Tensor:
-    return _Projection.apply(w, x)
 
 
 # ====================================================================== the fused block (hot path)

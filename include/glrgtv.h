@@ -241,16 +241,20 @@ int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params* p, const 
                      const glrgtv_block_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Feature projections patchs_features_extraction00 / 01 (V1X0:556-612, 712, 725): tensor-core GEMMs with 3xTF32
- * error compensation (fp32-level accuracy).  All operands row-major, contiguous, 16-byte aligned; M, N, K % 4 == 0.
- *   transpose_w == 0:  Y[b] (M x N) = W (M x K)   . X[b] (K x N)      forward of a 1x1 (or space-to-depth 2x2) conv
- *   transpose_w == 1:  Y[b] (K x N) = W^T (K x M) . X[b] (M x N)      its input gradient
+ * Feature projections patchs_features_extraction00 / 01 (V1X0:556-612, 712, 725; nn.Conv2d 1x1 and, after a
+ * space-to-depth, 2x2 stride 2) on the tcgen05 tensor cores (csrc/proj_tc.cu): kind::tf32 MMAs with TMEM accumulators,
+ * TMA operand loads, and the three-pass split a_hi b_hi + a_lo b_hi + a_hi b_lo (fp32-level accuracy, ~1e-6).
+ * All operands row-major, contiguous, 16-byte aligned; M, N (pixels), K % 4 == 0 (tiles are zero-padded by the TMA unit).
+ *   transpose_w == 0:  Y[b] (M x N) = W (M x K)   . X[b] (K x N)      forward
+ *   transpose_w == 1:  Y[b] (K x N) = W^T (K x M) . X[b] (M x N)      input gradient
+ * workspace: glrgtv_proj_gemm_workspace_bytes(M, K) bytes (the weights split into TF32 hi | lo parts).
  * ---------------------------------------------------------------------------------------------- */
+size_t glrgtv_proj_gemm_workspace_bytes(int M, int K);
 int glrgtv_proj_gemm(int transpose_w, int batch, int M, int N, int K, const float* W, const float* X, float* Y,
-                     void* stream);
-/* Weight gradient of the same projections: gW [M,K] += sum_b gY[b] (M x N) . X[b]^T (N x K), fp32 FMA, the reduction
- * over batch and pixels split across the grid (ACCUMULATES: the caller zeroes gW).  N % 32 == 0 and (M % 96 == 0,
- * K % 48 == 0) or (K % 96 == 0, M % 48 == 0); GLRGTV_ERR_UNSUPPORTED otherwise. */
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* Weight gradient of the same projections: gW [M,K] += sum_b gY[b] (M x N) . X[b]^T (N x K), same tensor-core scheme,
+ * the reduction over batch and pixels split across the grid and reduced with red.global.add (ACCUMULATES: the caller
+ * zeroes gW).  M, N, K % 4 == 0; GLRGTV_ERR_UNSUPPORTED otherwise. */
 int glrgtv_proj_wgrad(int batch, int M, int N, int K, const float* gY, const float* X, float* gW, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
