@@ -760,10 +760,35 @@ static size_t ws_floats(const glrgtv_shape* s, size_t* o_gx2, size_t* o_gx1, siz
     return off;
 }
 
+// second-generation backward (bw2.cu): five stage tensors (gx2, gA, gB, gx1, gbA), the half-resolution result vc, and the four
+// edge-weight gradient sets (accumulated by the stages with red.global.add: zeroed first)
+struct Bw2Ws {
+    size_t gx2, gA, gB, gx1, gbA, vc, gw, total;
+};
+static Bw2Ws bw2_ws(const glrgtv_shape* s) {
+    const size_t N = (size_t)s->B * s->H * s->W, C = (size_t)s->G * s->F, GE = (size_t)s->G * 4;
+    auto up = [](size_t v) { return (v + 3) & ~(size_t)3; };
+    Bw2Ws w;
+    size_t off = 0;
+    w.gx2 = off; off = up(off + C * N);
+    w.gA = off; off = up(off + C * N);
+    w.gB = off; off = up(off + C * N);
+    w.gx1 = off; off = up(off + C * N);
+    w.gbA = off; off = up(off + C * N);
+    w.vc = off; off = up(off + C * (N / 4));
+    w.gw = off; off = up(off + 2 * GE * N + 2 * GE * (N / 4));
+    w.total = off;
+    return w;
+}
+bool glr_bw2_eligible(const glrgtv_shape* s);
+extern int g_glr_bw2;
+
 extern "C" size_t glrgtv_block_bwd_workspace_bytes(const glrgtv_shape* s) {
     if (!glr_shape_ok(s)) return 0;
     size_t a, b, c, d, e;
-    return ws_floats(s, &a, &b, &c, &d, &e) * sizeof(float);
+    size_t n = ws_floats(s, &a, &b, &c, &d, &e);
+    if (glr_bw2_eligible(s)) { const size_t m = bw2_ws(s).total; n = m > n ? m : n; }
+    return n * sizeof(float);
 }
 
 int glr_block_params_ok(const glrgtv_shape* s, const glrgtv_block_params* p);
@@ -798,6 +823,40 @@ extern "C" int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params
 
     float* ws = (float*)workspace;
     const size_t N = (size_t)s->B * s->H * s->W, GE = (size_t)s->G * 4;
+    // second-generation pair walkers (bw2.cu): edge-weight gradients folded in, 2 launches per stage (half, full resolution)
+    if (g_glr_bw2 && g_glr_block_path != 1 && glr_bw2_eligible(s)) {
+        const Bw2Ws o = bw2_ws(s);
+        if (workspace_bytes < o.total * sizeof(float)) return GLRGTV_ERR_WORKSPACE;
+        float *gwT0 = ws + o.gw, *gwL0 = gwT0 + GE * N, *gwT1 = gwL0 + GE * N, *gwL1 = gwT1 + GE * (N / 4);
+        if (glr_memset_async(gwT0, 0, (2 * GE * N + 2 * GE * (N / 4)) * sizeof(float), (cudaStream_t)stream)) return GLRGTV_ERR_CUDA;
+        B2Args b = {};
+        b.s = *s; b.p = *p; b.gr = *gr;
+        b.wT = sv->wT0; b.wL = sv->wL0; b.gwT = gwT0; b.gwL = gwL0;
+        float *gx2 = ws + o.gx2, *gA = ws + o.gA, *gB = ws + o.gB, *gx1 = ws + o.gx1, *gbA = ws + o.gbA, *vc = ws + o.vc;
+        // X3: through x3 = x2 + a2 (r2 + b2 r1), r2 = bB - A x2
+        b.z = sv->x2; b.src = gout; b.op0 = sv->r1; b.op1 = sv->bB; b.op2 = x; b.out0 = gx2; b.out1 = gA; b.out2 = gB;
+        if ((rc = glr_bw2_stage<BW_X3>(b, sv->wT1, sv->wL1, gwT1, gwL1, vc, GLRGTV_SLOT_BWD_X3, stream))) return rc;
+        // X2: through x2 = x1 + a1 r1, r1 = bB - A x1 (part A) and bB = y + R_thr x1 (part B)
+        b.z = sv->x1; b.src = gA; b.op0 = sv->r1; b.op1 = gx2; b.op2 = nullptr; b.out0 = gx1; b.out1 = b.out2 = nullptr;
+        if ((rc = glr_bw2_stage<BW_X2A>(b, sv->wT1, sv->wL1, gwT1, gwL1, vc, GLRGTV_SLOT_BWD_X2, stream))) return rc;
+        b.src = gB; b.op0 = gx1; b.op1 = nullptr;
+        if ((rc = glr_bw2_stage<BW_X2B>(b, sv->wT1, sv->wL1, gwT1, gwL1, vc, GLRGTV_SLOT_BWD_X2, stream))) return rc;
+        // X1: through x1 = bA + a0 (bA - A bA)
+        b.z = sv->bA; b.src = gx1; b.op0 = nullptr; b.out0 = gbA;
+        if ((rc = glr_bw2_stage<BW_X1>(b, sv->wT1, sv->wL1, gwT1, gwL1, vc, GLRGTV_SLOT_BWD_X1, stream))) return rc;
+        // BA: through bA = y + R_lin y, plus the pointwise paths into y (bB, skip)
+        b.z = x; b.src = gbA; b.op0 = gB; b.op1 = gout; b.out0 = gx;
+        if ((rc = glr_bw2_stage<BW_BA>(b, sv->wT1, sv->wL1, gwT1, gwL1, vc, GLRGTV_SLOT_BWD_BA, stream))) return rc;
+        glrgtv_shape sc = *s;
+        sc.H /= 2; sc.W /= 2;
+        GLR_PROF_BEGIN(GLRGTV_SLOT_BWD_WEIGHTS, stream);
+        if ((rc = glr_block_weights_bwd(s, feat0, p->gtv0.multiM, p->glr0.multiM, sv->wT0, sv->wL0, gwT0, gwL0, gfeat0, gr->gtv0_M,
+                                        gr->glr0_M, stream))) return rc;
+        rc = glr_block_weights_bwd(&sc, feat1, p->gtv1.multiM, p->glr1.multiM, sv->wT1, sv->wL1, gwT1, gwL1, gfeat1, gr->gtv1_M,
+                                   gr->glr1_M, stream);
+        GLR_PROF_END(GLRGTV_SLOT_BWD_WEIGHTS, stream);
+        return rc;
+    }
     // register-streaming backward (block_stream_bwd.cu + block_gw.cu) where the shape allows, else the plane kernels
     const bool can_stream = glr_stream_fwd_eligible(s) && sv->cT0 && sv->cT1;     // any W % 8 == 0: wide planes in column strips
     if (g_glr_block_path == 2 && !can_stream) return GLRGTV_ERR_UNSUPPORTED;

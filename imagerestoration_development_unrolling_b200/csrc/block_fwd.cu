@@ -453,11 +453,13 @@ extern "C" int glrgtv_block_fwd(const glrgtv_shape* s, const glrgtv_block_params
     // register-streaming stage kernels (block_stream_fwd.cu) where the shape allows, else the plane kernels below
     const bool can_stream = glr_stream_fwd_eligible(s) && sv->cT0 && sv->cT1 && glr_aligned16(sv->cT0) && glr_aligned16(sv->cT1);
     if (g_glr_block_path == 2 && !can_stream) return GLRGTV_ERR_UNSUPPORTED;
-    if (can_stream && g_glr_block_path != 1) {
+    // the symmetric GTV coefficients are part of the saved state WHATEVER kernels run the stages: the backward may take the
+    // streaming kernels even when this forward took the plane kernels (it picks its path from the shape, not from this call)
+    if (sv->cT0 && sv->cT1) {
         if ((rc = glr_launch_gtv_coeffs(*s, sv->wT0, sv->cT0, stream))) return rc;
         if ((rc = glr_launch_gtv_coeffs(sc, sv->wT1, sv->cT1, stream))) return rc;
-        return glr_stream_block_fwd(s, p, x, out, sv, stream);
     }
+    if (can_stream && g_glr_block_path != 1) return glr_stream_block_fwd(s, p, x, out, sv, stream);
 
     BlockFwdArgs a;
     a.s = *s; a.p = *p;

@@ -50,10 +50,36 @@ def test_stream_block_forward(case):
     assert rel(out, ref_out) < 1e-5
 
 
-@pytest.mark.parametrize("gw_streaming", [0, 1], ids=["gw_tiled", "gw_stream"])
-@pytest.mark.parametrize("case", CASES + [(3, 1, 1, 6, 272), (2, 1, 1, 4, 504)])
+# second-generation pair walkers (csrc/bw2.cu): extra shapes - wide walkers with seams (W = 256: four warps per row), ragged
+# widths, several channels per warp, row bands, F = 12
+BW2_CASES = CASES + [(3, 1, 1, 6, 272), (2, 1, 1, 4, 504), (6, 1, 1, 8, 256), (12, 1, 1, 6, 64), (6, 2, 2, 60, 8), (3, 1, 1, 100, 24),
+                     (12, 1, 1, 6, 128), (6, 1, 2, 10, 136), (24, 2, 1, 6, 32)]
+
+
+def bw2_eligible(F, H, W):
+    """mirror of glr_bw2_eligible (csrc/bw2.cu): W % 8 == 0, a CTA of <= 384 threads holds at least half of a graph's channels
+    (>= 2 of them: two weight-plane copies per thread) at both resolutions"""
+    if W % 8 or H % 2 or W < 8 or H < 4:
+        return False
+    for lw in (W, W // 2):
+        lanes = 4
+        while 2 * lanes < lw:
+            lanes *= 2
+        nch = max([n for n in range(1, F + 1) if F % n == 0 and n * lanes <= 384], default=0)
+        if nch < 2 or F // nch > 2:
+            return False
+    return True
+
+
+@pytest.mark.parametrize("gw_streaming", [0, 1, 2], ids=["gw_tiled", "gw_stream", "bw2"])
+@pytest.mark.parametrize("case", BW2_CASES)
 def test_stream_block_backward(case, gw_streaming):
     dim, G, B, H, W = case
+    bw2 = gw_streaming == 2
+    if not bw2 and case not in CASES + [(3, 1, 1, 6, 272), (2, 1, 1, 4, 504)]:
+        pytest.skip("round-1 kernels: covered by their own cases")
+    E.emu_lib().glrgtv_set_bwd_kernels(2 if bw2 else 1)
+    gw_streaming = 0 if bw2 else gw_streaming
     E.emu_lib().glrgtv_set_gw_kernel(gw_streaming)
     F = dim // G
     sd = random_block_state(dim, G, seed=400 + H)
@@ -76,7 +102,10 @@ def test_stream_block_backward(case, gw_streaming):
     gx, gf0, gf1 = torch.empty_like(x), torch.empty_like(f0), torch.empty_like(f1)
     n0 = E.emu_lib().glrgtv_stream_launch_count()
     E.call("glrgtv_block_bwd", shp, p, x, f0.detach(), f1.detach(), sv, gout, gx, gf0, gf1, gr, ws, nbytes, None)
-    assert E.emu_lib().glrgtv_stream_launch_count() - n0 == 13      # 5 stage kernels + 4 x 2 edge-weight-gradient kernels
+    E.emu_lib().glrgtv_set_bwd_kernels(2)
+    nl = E.emu_lib().glrgtv_stream_launch_count() - n0
+    # round 1: 5 stage kernels + 4 x 2 edge-weight-gradient kernels; bw2: 5 stages x (half + full resolution), no gradient pass
+    assert nl == (10 if bw2 and bw2_eligible(F, H, W) else 13), nl
     names = list(pw)
     gfeat = torch.autograd.grad([f0, f1], [xx] + [pw[k] for k in names], [gf0, gf1])
     gx_total = gx + gfeat[0]

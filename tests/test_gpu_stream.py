@@ -24,6 +24,7 @@ def lib():
     yield lib
     lib.glrgtv_set_block_path(0)
     lib.glrgtv_set_stream_loader(0)
+    lib.glrgtv_set_bwd_kernels(2)
 
 
 # every walker width (8 / 16 / 32 / 64 lanes), partial walkers, F = 6 and 12, several channels per CTA
@@ -33,9 +34,12 @@ CASES = [(48, 8, 2, 32, 256), (96, 16, 1, 20, 128), (24, 2, 1, 36, 72), (192, 16
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("loader", [1, 2], ids=["cp_async", "tma"])
+@pytest.mark.parametrize("loader", [1, 2, 3], ids=["cp_async", "tma", "round1_bwd"])
 def test_streaming_path_against_oracle(M, lib, case, loader):
     dim, G, B, H, W = case
+    if loader == 3:                         # the round-1 backward kernels (block_stream_bwd.cu + block_gw.cu) stay a tested path
+        lib.glrgtv_set_bwd_kernels(1)
+        loader = 1
     sd = random_block_state(dim, G, seed=dim + H + W)
     gen = torch.Generator().manual_seed(3 * H + W)
     x, gout = torch.randn(B, dim, H, W, generator=gen), torch.randn(B, dim, H, W, generator=gen)
@@ -44,7 +48,9 @@ def test_streaming_path_against_oracle(M, lib, case, loader):
     lib.glrgtv_set_stream_loader(loader)
     n0 = lib.glrgtv_stream_launch_count()
     out, gx, pg = run_block(make_block(M, dim, G, sd), x, gout)
-    assert lib.glrgtv_stream_launch_count() - n0 == 4 + 13      # 4 forward stages; 5 backward stages + 8 gradient kernels
+    # 4 forward stages; backward: 5 stages x (half + full resolution) with the pair walkers of csrc/bw2.cu (edge-weight gradients
+    # folded in), or 5 stages + 8 gradient kernels with the round-1 kernels (shapes the pair walkers do not take)
+    assert lib.glrgtv_stream_launch_count() - n0 in (4 + 10, 4 + 13)
     check_against(out, gx, pg, *ref)
 
 
@@ -57,6 +63,7 @@ def test_streaming_gradient_kernel_against_oracle(M, lib, case):
     x, gout = torch.randn(B, dim, H, W, generator=gen), torch.randn(B, dim, H, W, generator=gen)
     ref = O.lowpass_block_fwd_bwd({k: v.double() for k, v in sd.items()}, x.double(), gout.double())
     lib.glrgtv_set_block_path(2)
+    lib.glrgtv_set_bwd_kernels(1)             # the round-1 backward (the pair walkers have no separate gradient kernel)
     lib.glrgtv_set_gw_kernel(1)
     try:
         out, gx, pg = run_block(make_block(M, dim, G, sd), x, gout)
@@ -213,3 +220,25 @@ def test_cuda_stage_runner_single_rank(M, lib):
         ref = blk(x)
         got = shard.sharded_block_forward_staged(blk, x, 0, 1, runner=shard.CudaStageRunner(blk))
     assert rel(got, ref) < 1e-6
+
+
+@pytest.mark.parametrize("scale", [0, 1, 2, 3])
+def test_pair_walkers_equal_round1_kernels_at_benchmark_size(M, lib, scale):
+    """csrc/bw2.cu (compile-time geometry kernels of the v13 configuration, two CTAs per graph at scale 0) against the round-1
+    backward at the benchmark's plane sizes: every gradient, relative L2"""
+    dim, G = [48, 96, 192, 384][scale], [8, 16, 16, 32][scale]
+    B, H = 2, 256 >> scale
+    sd = random_block_state(dim, G, seed=21 + scale)
+    gen = torch.Generator().manual_seed(9 + scale)
+    x, gout = torch.randn(B, dim, H, H, generator=gen), torch.randn(B, dim, H, H, generator=gen)
+    blk = make_block(M, dim, G, sd)
+    lib.glrgtv_set_bwd_kernels(1)
+    out1, gx1, pg1 = run_block(blk, x, gout)
+    lib.glrgtv_set_bwd_kernels(2)
+    n0 = lib.glrgtv_stream_launch_count()
+    out2, gx2, pg2 = run_block(blk, x, gout)
+    assert lib.glrgtv_stream_launch_count() - n0 == 4 + 10
+    assert rel(gx2, gx1) < 5e-6, rel(gx2, gx1)
+    for k in pg1:
+        if float(pg1[k].abs().max()) > 0:
+            assert rel(pg2[k], pg1[k]) < 2e-4, (k, rel(pg2[k], pg1[k]))
