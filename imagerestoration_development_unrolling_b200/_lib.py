@@ -74,7 +74,6 @@ _SIGS = {
     "glrgtv_set_block_path": (C.c_int, [C.c_int]),
     "glrgtv_set_stream_loader": (C.c_int, [C.c_int]),
     "glrgtv_stream_launch_count": (C.c_ulonglong, []),
-    "glrgtv_set_gw_kernel": (C.c_int, [C.c_int]),
     "glrgtv_set_bwd_kernels": (C.c_int, [C.c_int]),
     "glrgtv_profile_read": (C.c_int, [_P(C.c_float), _P(C.c_int), C.c_int]),
     "glrgtv_edge_weights_fwd": (C.c_int, [_P(Shape), _P(Window), fp, fp, fp, fp]),

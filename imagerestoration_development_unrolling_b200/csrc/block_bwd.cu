@@ -731,16 +731,9 @@ static int launch_bwd_stage(const BlockBwdArgs& a, void* stream) {
     return (a.s.W % 8 == 0) ? launch_bwd_stage_gen<MODE, false>(a, stream) : launch_bwd_stage_gen<MODE, true>(a, stream);
 }
 
-// edge-weight gradients of one stage: the streaming kernels where they apply, else the tiled kernel
-extern int g_glr_gw_tiled;
+// edge-weight gradients of one stage of the round-1 backward: the tiled kernel of block_gw.cu
 template <int MODE>
-static int gw_stage(const GwArgs& w, int slot, void* stream) {
-    if (!g_glr_gw_tiled) {
-        const int rc = glr_gw_stream_stage<MODE>(w, slot, stream);
-        if (rc != GLRGTV_ERR_UNSUPPORTED) return rc;
-    }
-    return glr_gw_stage<MODE>(w, slot, stream);
-}
+static int gw_stage(const GwArgs& w, int slot, void* stream) { return glr_gw_stage<MODE>(w, slot, stream); }
 
 // tiled edge-weight backward of one resolution (block_weights_bwd.cu)
 int glr_block_weights_bwd(const glrgtv_shape* s, const float* feat, const float* M_gtv, const float* M_glr,

@@ -196,11 +196,6 @@ __global__ void __launch_bounds__(GQ_NT, GQ_MINB) k_gw_quad(GwArgs a) {
 }
 
 extern unsigned long long g_glr_stream_launches;
-// 1 (default): the tiled kernel below; 0: the streaming form (block_gw_stream.cu) where its range allows.  Measured on
-// B200 at the benchmark sizes the streaming form is level with the tiled one for X3 / X1 / BA and slower for X2 (its
-// 768-thread CTA pays one block barrier per row), so the tiled kernel stays the default.
-int g_glr_gw_tiled = 1;
-extern "C" int glrgtv_set_gw_kernel(int streaming) { g_glr_gw_tiled = streaming ? 0 : 1; return GLRGTV_OK; }
 template <int MODE>
 int glr_gw_stage(const GwArgs& a, int slot, void* stream) {
     const glrgtv_shape& s = a.s;

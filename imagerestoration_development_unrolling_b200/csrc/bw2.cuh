@@ -57,6 +57,7 @@ __device__ __forceinline__ float2 pshr(float2 c, float r) { return make_float2(c
 #define B2_ZR 8          // ring rows of the stage input / upstream gradient (rows t-4 .. t+2 are live)
 #define B2_ZRC 4         // COARSE: ring rows of the staged full-resolution rows (pooled at arrival into rings of B2_ZR rows)
 #define B2_WR 4          // ring rows of the weight planes
+#define B2_OPR 4         // ring rows of the epilogue operands
 #define B2_NFLD 6        // seam mailbox fields: s_T s_L h_T h_L gs_T gs_L
 #ifndef B2_MAXT
 #define B2_MAXT 384
@@ -73,13 +74,17 @@ template <int MODE, bool COARSE>
 struct B2Smem {
     static constexpr bool HAS_L = MODE == BW_X3 || MODE == BW_X2A || MODE == BW_X1, THR = MODE == BW_X2B;
     static constexpr int NPT = 4, NPLW = NPT + (HAS_L ? 4 : 0), NGW = 4 + (HAS_L ? 4 : 0);
+    // epilogue operand tensors of the full-resolution launch (X3: r1, bB, x; X2A: r1, gx2; X2B: gx1; BA: gB, gout)
+    static constexpr int NOP = COARSE ? 0 : MODE == BW_X3 ? 3 : (MODE == BW_X2A || MODE == BW_BA) ? 2 : MODE == BW_X2B ? 1 : 0;
     int NCH, L;       // channels per CTA, lanes per row
     __host__ __device__ int rw() const { return 2 * L; }
     __host__ __device__ size_t zsig() const { return 0; }                                                    // [NCH][ZR][RW] level rows of z
     __host__ __device__ size_t gsig() const { return zsig() + (size_t)NCH * B2_ZR * rw(); }                 // [NCH][ZR][RW] level rows of g
     __host__ __device__ size_t zstage() const { return gsig() + (size_t)NCH * B2_ZR * rw(); }               // COARSE [NCH][ZRC][2][2 RW] full-resolution rows
     __host__ __device__ size_t gstage() const { return zstage() + (COARSE ? (size_t)NCH * B2_ZRC * 4 * rw() : 0); }
-    __host__ __device__ size_t wring() const { return gstage() + (COARSE ? (size_t)NCH * B2_ZRC * 4 * rw() : 0); }   // [NPLW][WR][RW]
+    __host__ __device__ size_t opring() const { return gstage() + (COARSE ? (size_t)NCH * B2_ZRC * 4 * rw() : 0); }  // [NOP][NCH][4][RW]
+    __host__ __device__ size_t vcring() const { return opring() + (size_t)NOP * NCH * B2_OPR * rw(); }              // fine: [NCH][4][RW/2]
+    __host__ __device__ size_t wring() const { return vcring() + (COARSE ? 0 : (size_t)NCH * B2_OPR * (rw() / 2)); }  // [NPLW][WR][RW]
     __host__ __device__ size_t gwpost() const { return wring() + (size_t)NPLW * B2_WR * rw(); }             // [2][NCH][NGW][RW]
     __host__ __device__ size_t mbox() const { return gwpost() + (size_t)2 * NCH * NGW * rw(); }             // [2][NCH][warps per row][NFLD][2]
     __host__ __device__ size_t scratch() const { return (mbox() + (size_t)2 * NCH * ((L + 31) / 32) * B2_NFLD * 2 + 3) & ~(size_t)3; }
@@ -217,21 +222,34 @@ __global__ void __launch_bounds__(B2_MAXT, B2_MINB) k_bw2(B2Args a) {
     //      the two full-resolution rows of its own four columns.  Weights: up to two 16-byte pieces of plane rows per thread
     //      (4 NCH >= planes); plane U of a raw set runs one row ahead (its row r + 1 feeds the cores of row r).
     int tl = R0 - 3;                                  // the row the next issue() stages
-    const float* zp = a.z;                            // -> this thread's piece of row clamp(tl)
+    // (global addresses = tensor base + a 32-bit element offset that advances by one row per step)
+    const float* zbase = a.z;
+    unsigned zo = 0;                                  // offset of this thread's piece of row clamp(tl)
     float* zdst = smem;
     bool zok = false;
     if (COARSE) {
         zok = live && 4 * lr < W;
-        zp = a.z + pl_f * a.s.H * W + (size_t)(2 * glr_clampi(tl, 0, LH - 1)) * W + (zok ? 4 * lr : 0);
+        zo = (unsigned)(pl_f * a.s.H * W) + (unsigned)(2 * glr_clampi(tl, 0, LH - 1) * W + (zok ? 4 * lr : 0));
         zdst = smem + lay.zstage() + ((size_t)chc * B2_ZRC * 4 << LG) + 4 * lr;
     } else {
         const int cc = 2 * (lr & ~1);
         zok = live && cc < W;
-        zp = ((lr & 1) ? a.src : a.z) + pl_f * a.s.H * W + (size_t)glr_clampi(tl, 0, LH - 1) * W + (zok ? cc : 0);
+        zbase = (lr & 1) ? a.src : a.z;
+        zo = (unsigned)(pl_f * a.s.H * W) + (unsigned)(glr_clampi(tl, 0, LH - 1) * W + (zok ? cc : 0));
         zdst = smem + ((lr & 1) ? lay.gsig() : lay.zsig()) + ((size_t)chc * B2_ZR << LG) + cc;
     }
     const bool zisz = COARSE || !(lr & 1);            // this thread's fine-level copy is a z row (clamped) / a g row (zero-filled outside)
-    const float* wp[2] = {a.wT, a.wT};
+    // epilogue operands (full resolution only): the even lane of a piece copies operand 0 and 2, the odd lane operand 1, for the
+    // epilogue row of the step the z / g rows are staged for (tl - 4), through 32-bit element offsets from the tensor bases
+    constexpr int NOP = SM::NOP;
+    float* const opdst = smem + lay.opring() + ((size_t)chc * B2_OPR << LG) + 2 * (lr & ~1);
+    unsigned ooff = (unsigned)(pl_f * a.s.H * W) + (unsigned)((tl - 4) * W + 2 * (lr & ~1));
+    // the half-resolution launch's result: one 16-byte piece (4 of its pixels = the pairs of 4 lanes) per even epilogue row,
+    // copied by the lane with lr % 4 == 3
+    float* const vcdst = smem + lay.vcring() + ((size_t)chc * B2_OPR << (LG - 1)) + (lr & ~3);
+    unsigned vcoff = (unsigned)(pl_f * (LH / 2) * (LW / 2)) + (unsigned)(((tl - 4) >> 1) * (LW / 2) + (lr & ~3));
+    const float* wbase[2] = {a.wT, a.wT};
+    unsigned wo[2] = {0, 0};
     float* wdst[2] = {smem, smem};
     bool wok[2] = {false, false};
     int wlead[2] = {0, 0};
@@ -243,31 +261,43 @@ __global__ void __launch_bounds__(B2_MAXT, B2_MINB) k_bw2(B2Args a) {
             const bool isL = pl >= NPT;
             const int e = isL ? pl - NPT : pl;
             wlead[j] = e == 0 ? 1 : 0;
-            const float* base = (isL ? a.wL : a.wT) + plane * 4 * LH * LW;
-            wp[j] = base + (size_t)e * LH * LW + (size_t)glr_clampi(tl - 2 + wlead[j], 0, LH - 1) * LW + 4 * piece;
+            wbase[j] = isL ? a.wL : a.wT;
+            wo[j] = (unsigned)((plane * 4 + e) * LH * LW) + (unsigned)(glr_clampi(tl - 2 + wlead[j], 0, LH - 1) * LW + 4 * piece);
             wdst[j] = smem + lay.wring() + ((size_t)pl * B2_WR << LG) + 4 * piece;
             wok[j] = true;
         }
     }
-    const long gdelta = COARSE ? (long)(a.src - a.z) : 0;                         // coarse: g pieces sit at the same offsets as z's
     const int sdelta = COARSE ? (int)(lay.gstage() - lay.zstage()) : 0;
     auto issue = [&]() {                             // the copies of row tl; pointers advance to the next row unless it is clamped
         const bool in = (unsigned)tl < (unsigned)LH;
         if (zok) {
             if (COARSE) {
                 float* d = zdst + ((tl & (B2_ZRC - 1)) * 4 << LG);
-                cp_async16(d, zp); cp_async16(d + RW * 2, zp + W);
-                b2_cp16(d + sdelta, zp + gdelta, in); b2_cp16(d + sdelta + RW * 2, zp + gdelta + W, in);
+                cp_async16(d, a.z + zo); cp_async16(d + RW * 2, a.z + zo + W);
+                b2_cp16(d + sdelta, a.src + zo, in); b2_cp16(d + sdelta + RW * 2, a.src + zo + W, in);
             } else {
-                b2_cp16(zdst + ((tl & (B2_ZR - 1)) << LG), zp, in || zisz);
+                b2_cp16(zdst + ((tl & (B2_ZR - 1)) << LG), zbase + zo, in || zisz);
             }
         }
-        if (tl >= 0 && tl < LH - 1) zp += COARSE ? 2 * W : W;
+        if (tl >= 0 && tl < LH - 1) zo += COARSE ? 2 * W : W;
+        if (NOP > 0 && zok && tl - 4 >= R0 && tl - 4 < R1) {
+            float* d = opdst + (((tl - 4) & (B2_OPR - 1)) << LG);
+            if (lr & 1) {
+                if (NOP > 1) cp_async16(d + (NCH * B2_OPR << LG), a.op1 + ooff);
+            } else {
+                cp_async16(d, a.op0 + ooff);
+                if (NOP > 2 && a.op2 != nullptr) cp_async16(d + (2 * NCH * B2_OPR << LG), a.op2 + ooff);
+            }
+        }
+        ooff += W;
+        if (!COARSE && live && (lr & 3) == 3 && (lr & ~3) < LW / 2 && !((tl - 4) & 1) && tl - 4 >= R0 - 1 && tl - 4 < R1)      // (a band may start on an odd row)
+            cp_async16(vcdst + ((((tl - 4) >> 1) & (B2_OPR - 1)) << (LG - 1)), a.vc_in + vcoff);
+        if ((tl - 4) & 1) vcoff += LW / 2;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int rw_ = tl - 2 + wlead[j];
-            if (wok[j]) b2_cp16(wdst[j] + ((rw_ & (B2_WR - 1)) << LG), wp[j], (unsigned)rw_ < (unsigned)LH);
-            if (rw_ >= 0 && rw_ < LH - 1) wp[j] += LW;
+            if (wok[j]) b2_cp16(wdst[j] + ((rw_ & (B2_WR - 1)) << LG), wbase[j] + wo[j], (unsigned)rw_ < (unsigned)LH);
+            if (rw_ >= 0 && rw_ < LH - 1) wo[j] += LW;
         }
         ++tl;
     };
@@ -293,15 +323,15 @@ __global__ void __launch_bounds__(B2_MAXT, B2_MINB) k_bw2(B2Args a) {
     int zt = (t & (B2_ZR - 1)) << LG;                 // ring slot of row t in the level rings
     int wt = ((t - 2) & (B2_WR - 1)) << LG;           // ring slot of row t-2 in the weight rings
     const int POSTS = (NCH * NGW) << LG, MBS = NCH * NWR * B2_NFLD * 2;
-    float* postw = live ? smem + lay.gwpost() + ((size_t)chc * NGW << LG) + col0 : smem + lay.scratch() + col0;      // this step's posts
-    const float* postr = smem + lay.gwpost() + POSTS + col0;                                                          // last step's posts
-    float* mbw = smem + lay.mbox() + (chc * NWR + (lr >> 5)) * B2_NFLD * 2;
-    const float* mbr = mbw + MBS;
+    // double buffers: what a step posts (gradient products, seam scalars) is read in the next step
+    float* const postw0 = live ? smem + lay.gwpost() + ((size_t)chc * NGW << LG) + col0 : smem + lay.scratch() + col0;
+    const float* const postr0 = smem + lay.gwpost() + col0;
+    float* const mb0 = smem + lay.mbox() + (chc * NWR + (lr >> 5)) * B2_NFLD * 2;
+    int pofs = 0, mofs = 0;                           // this step's buffer (0 / POSTS, 0 / MBS)
     // global element offset of (this channel, row t-4, col0) in the full-resolution tensors / the level tensors
     // (32-bit element offsets: tensors of up to 2^32 elements; they wrap harmlessly while the row is outside the band)
     unsigned goff = (unsigned)(pl_f * a.s.H * W) + (unsigned)((t - 4) * W + col0);
     unsigned loff = (unsigned)(pl_f * LH * LW) + (unsigned)((t - 4) * LW + col0);
-    unsigned voff = (unsigned)(pl_f * (LH / 2) * (LW / 2)) + (unsigned)(((t - 4) >> 1) * (LW / 2) + lr);
     unsigned gwoff = (unsigned)(plane * 4 * LH * LW) + (unsigned)((t - 3) * LW + col0);
     const unsigned HWl = (unsigned)(LH * LW);
 
@@ -315,18 +345,13 @@ __global__ void __launch_bounds__(B2_MAXT, B2_MINB) k_bw2(B2Args a) {
         issue();
         cp_async_commit();
         const int o1 = (zt - RW) & M8, o2 = (zt - 2 * RW) & M8, o3 = (zt - 3 * RW) & M8, o4 = (zt - 4 * RW) & M8;
+        float* const postw = postw0 + (live ? pofs : 0);
+        const float* const postr = postr0 + (POSTS - pofs);
+        float* const mbw = mb0 + mofs;
+        const float* const mbr = mb0 + (MBS - mofs);
 
-        // ---- epilogue operands of row t-4: issue the global loads now, use them at the end of the step
         const int rf = t - 4;
         const bool fin = active && rf >= R0 && rf < R1;
-        float2 q0 = pzero(), q1 = pzero(), q2 = pzero();
-        float vcv = 0.f;
-        if (!COARSE && fin) {
-            if (MODE != BW_X1) q0 = pld(a.op0 + goff);
-            if (MODE == BW_X3 || MODE == BW_X2A || MODE == BW_BA) q1 = pld(a.op1 + goff);
-            if (MODE == BW_X3 && has_skip) q2 = pld(a.op2 + goff);
-            vcv = a.vc_in[voff];
-        }
 
         // ---- edge-weight gradients of row t-3: sum last step's posts over the channels (thread (ch, lr): planes ch, ch+NCH, ..)
         if (t - 3 >= R0 && t - 3 < R1 && active) {
@@ -525,6 +550,12 @@ __global__ void __launch_bounds__(B2_MAXT, B2_MINB) k_bw2(B2Args a) {
                 pst(a.vc_out + loff, Vdone);
             } else {
                 const float2 gq = pld(gsig + o4), zq = pld(zsig + o4);
+                const float* ops = opdst - 2 * (lr & ~1) + col0 + ((rf & (B2_OPR - 1)) << LG);
+                float2 q0 = pzero(), q1 = pzero(), q2 = pzero();
+                if (NOP > 0) q0 = pld(ops);
+                if (NOP > 1) q1 = pld(ops + (NCH * B2_OPR << LG));
+                if (NOP > 2 && has_skip) q2 = pld(ops + (2 * NCH * B2_OPR << LG));
+                const float vcv = vcdst[(((rf >> 1) & (B2_OPR - 1)) << (LG - 1)) + (lr & 3)];
                 float2 Wp = pfmas(pset(vcv), 0.25f, Vdone);
                 if (HAS_L) Wp = padd(Wp, gq);
                 if (MODE == BW_X3) {              // gq gout, q0 r1, q1 bB, q2 x, zq x2
@@ -558,10 +589,8 @@ __global__ void __launch_bounds__(B2_MAXT, B2_MINB) k_bw2(B2Args a) {
         zt = (zt + RW) & M8;
         wt = (wt + RW) & M4;
         goff += W; loff += LW; gwoff += LW;
-        if (!(t & 1)) voff += LW / 2;                     // (t was just incremented: row t-4 is even again)
-        // swap the double buffers: posts and mailboxes written in this step are read in the next
-        if (m & 1) { postr += POSTS; mbr += MBS; mbw -= MBS; if (live) postw -= POSTS; }
-        else { postr -= POSTS; mbr -= MBS; mbw += MBS; if (live) postw += POSTS; }
+        pofs = POSTS - pofs;
+        mofs = MBS - mofs;
     }
     cp_async_wait_all();
 
@@ -657,9 +686,19 @@ static int b2_launch(B2Args a, int slot, void* stream) {
     B2Smem<MODE, COARSE> lay; lay.NCH = a.nch; lay.L = L;
     const size_t smem = lay.bytes();
     if (threads > B2_MAXT || smem > 227 * 1024) return GLRGTV_ERR_UNSUPPORTED;
-    // row bands when one CTA per (batch, graph) would leave SMs idle
+    // row bands: the split that minimises (waves of CTAs) x (steps of one CTA); a band pays 7 pipeline-fill steps
+    int occ = (int)(227 * 1024 / (smem + 1024));
+    if (occ > B2_MAXT / threads) occ = B2_MAXT / threads;       // register file: the kernels are built for B2_MAXT threads per SM
+    if (occ < 1) occ = 1;
     int bands = 1;
-    while ((long)s.B * s.G * a.n_parts * bands < 2 * 148 && LH / (bands * 2) >= 24) bands *= 2;
+    {
+        const long base = (long)s.B * s.G * a.n_parts, slots = 148L * occ;
+        long best = -1;
+        for (int bnd = 1; bnd <= 8 && LH / bnd >= 24; bnd *= 2) {
+            const long cost = ((base * bnd + slots - 1) / slots) * ((LH + bnd - 1) / bnd + 7);
+            if (best < 0 || cost < best) { best = cost; bands = bnd; }
+        }
+    }
     a.band_rows = (LH + bands - 1) / bands;
     a.n_bands = (LH + a.band_rows - 1) / a.band_rows;
     const long blocks = (long)s.B * s.G * a.n_parts * a.n_bands;

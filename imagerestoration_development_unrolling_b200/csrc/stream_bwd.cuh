@@ -34,8 +34,6 @@ struct GwArgs {
 
 template <int MODE> int glr_stream_bwd_stage(StreamBwdArgs a, int slot, void* stream);
 template <int MODE> int glr_gw_stage(const GwArgs& a, int slot, void* stream);
-// streaming form (block_gw_stream.cu); GLRGTV_ERR_UNSUPPORTED when the shape is outside its range
-template <int MODE> int glr_gw_stream_stage(const GwArgs& a, int slot, void* stream);
 
 // ---- second-generation backward stages (bw2.cu)
 struct B2Args {

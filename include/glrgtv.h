@@ -210,9 +210,6 @@ int glrgtv_set_block_path(int mode);
 /* Loader of the streaming kernels: 0 = automatic (per stage, as measured), 1 = per-thread cp.async rings,
  * 2 = one producer warp issuing TMA bulk row copies (cp.async.bulk + mbarrier).  Same results; a tuning switch. */
 int glrgtv_set_stream_loader(int mode);
-/* Edge-weight gradient kernel of the streaming backward: 0 = tiled (block_gw.cu, default), 1 = streaming walkers
- * (block_gw_stream.cu) where their range allows.  Same results; a tuning switch. */
-int glrgtv_set_gw_kernel(int streaming);
 /* Backward stage kernels: 2 (default) = the pair walkers of csrc/bw2.cu (packed fp32 arithmetic, edge-weight gradients folded
  * into the adjoint walk; W % 4 == 0, all channels of a graph in one CTA), 1 = the round-1 walkers + separate gradient pass.
  * Same results; a test / comparison switch. */

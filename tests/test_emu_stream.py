@@ -71,16 +71,14 @@ def bw2_eligible(F, H, W):
     return True
 
 
-@pytest.mark.parametrize("gw_streaming", [0, 1, 2], ids=["gw_tiled", "gw_stream", "bw2"])
+@pytest.mark.parametrize("generation", [1, 2], ids=["round1", "bw2"])
 @pytest.mark.parametrize("case", BW2_CASES)
-def test_stream_block_backward(case, gw_streaming):
+def test_stream_block_backward(case, generation):
     dim, G, B, H, W = case
-    bw2 = gw_streaming == 2
+    bw2 = generation == 2
     if not bw2 and case not in CASES + [(3, 1, 1, 6, 272), (2, 1, 1, 4, 504)]:
         pytest.skip("round-1 kernels: covered by their own cases")
-    E.emu_lib().glrgtv_set_bwd_kernels(2 if bw2 else 1)
-    gw_streaming = 0 if bw2 else gw_streaming
-    E.emu_lib().glrgtv_set_gw_kernel(gw_streaming)
+    E.emu_lib().glrgtv_set_bwd_kernels(generation)
     F = dim // G
     sd = random_block_state(dim, G, seed=400 + H)
     gen = torch.Generator().manual_seed(H * W + 1)
@@ -113,7 +111,6 @@ def test_stream_block_backward(case, gw_streaming):
     got.update({k: g for k, g in zip(names, gfeat[1:])})
     errs = {k: (rel(got[k], ref) if float(ref.abs().max()) > 0 else float(got[k].abs().max())) for k, ref in pg_ref.items()}
     errs["gx"] = rel(gx_total, gx_ref)
-    E.emu_lib().glrgtv_set_gw_kernel(0)
     bad = {k: v for k, v in errs.items() if v > 2e-4}
     assert not bad, bad
 

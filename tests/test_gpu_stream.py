@@ -54,24 +54,6 @@ def test_streaming_path_against_oracle(M, lib, case, loader):
     check_against(out, gx, pg, *ref)
 
 
-@pytest.mark.parametrize("case", [(48, 8, 2, 64, 256), (96, 16, 1, 40, 128), (192, 16, 1, 16, 32)])
-def test_streaming_gradient_kernel_against_oracle(M, lib, case):
-    """the opt-in streaming form of the edge-weight gradient kernel (block_gw_stream.cu)"""
-    dim, G, B, H, W = case
-    sd = random_block_state(dim, G, seed=dim + W)
-    gen = torch.Generator().manual_seed(H + W)
-    x, gout = torch.randn(B, dim, H, W, generator=gen), torch.randn(B, dim, H, W, generator=gen)
-    ref = O.lowpass_block_fwd_bwd({k: v.double() for k, v in sd.items()}, x.double(), gout.double())
-    lib.glrgtv_set_block_path(2)
-    lib.glrgtv_set_bwd_kernels(1)             # the round-1 backward (the pair walkers have no separate gradient kernel)
-    lib.glrgtv_set_gw_kernel(1)
-    try:
-        out, gx, pg = run_block(make_block(M, dim, G, sd), x, gout)
-    finally:
-        lib.glrgtv_set_gw_kernel(0)
-    check_against(out, gx, pg, *ref)
-
-
 @pytest.mark.parametrize("case", [(48, 8, 4, 256, 256), (96, 16, 4, 128, 128)])
 def test_streaming_equals_plane_kernels_at_benchmark_resolution(M, lib, case):
     """two independent CUDA implementations of the path (different tiling, different order of summation)"""
