@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH, help="per-rank batch (default = the config's 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-infer4k", action="store_true")
     return ap.parse_args()
 
 
@@ -172,14 +173,18 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ roofline bookkeeping
 SLOTS = ["fwd_weights", "fwd_BA", "fwd_X1", "fwd_X2", "fwd_X3", "bwd_X3", "bwd_X2", "bwd_X1", "bwd_BA", "bwd_weights",
-         "gw_X3", "gw_X2", "gw_X1", "gw_BA"]
+         "proj_fwd", "proj_dgrad", "proj_wgrad", "gw"]
 
 
 def algorithmic_bytes(slot, B):
     """fp32 bytes one step moves through the kernels of `slot`, summed over the four scales: every operand tensor read
     once + every result written once; halo re-reads and L2 hits are not algorithmic.
     C = channels, GE = 4G edge-weight planes of one set at full resolution; 1.25 = fine + quarter-size coarse set;
-    the symmetric GTV coefficients cT are half a set (0.625 GE with its coarse part)."""
+    the symmetric GTV coefficients cT are half a set (0.625 GE with its coarse part).
+    Backward stages (csrc/bw2.cu, a half-resolution and a full-resolution launch each): the half-resolution launch reads z and g
+    at full resolution (pooled on the fly, 2C) and writes its result vc (C/4), which the full-resolution launch reads back; the
+    raw weight sets are read (GE each, x1.25) and the edge-weight gradients accumulated with red.global.add (read + write:
+    2 GE per set, x1.25)."""
     total = 0
     for s, (C, G) in enumerate(zip(DIMS, NGRAPHS)):
         N = B * (RES >> s) * (RES >> s)
@@ -190,15 +195,17 @@ def algorithmic_bytes(slot, B):
             "fwd_X1": 2 * C + 1.875 * GE,                               # bA, wL, cT -> x1
             "fwd_X2": 5 * C + 3.125 * GE,                               # x1, y, wL, cT, wT -> x2, bB, r1
             "fwd_X3": 5 * C + 1.875 * GE,                               # x2, bB, r1, x, wL, cT -> out
-            "bwd_X3": 6 * C + 1.875 * GE,                               # gout, x2, bB, r1, x, wL, cT -> gx2
-            "bwd_X2": 10 * C + 3.125 * GE,                              # A: x1, gout, gx2, r1 -> gx1 ; B: x1, gout, gx2, gx1 -> gx1
-            "bwd_X1": 3 * C + 1.875 * GE,                               # bA, gx1, wL, cT -> gbA
-            "bwd_BA": 5 * C + 0.625 * GE,                               # y, gbA, gout, gx2, cT -> gx
+            # x2, gout, r1, bB, x -> gx2, gA, gB (8C) + coarse re-read 2C + vc 0.5C; wT, wL 2.5 GE; gwT, gwL += 5 GE
+            "bwd_X3": 10.5 * C + 7.5 * GE,
+            # A: x1, gA, r1, gx2 -> gx1 (5C + 2.5C); B: x1, gB, gx1 -> gx1 (4C + 2.5C), GTV only: wT 1.25 GE, gwT += 2.5 GE
+            "bwd_X2": 14 * C + 11.25 * GE,
+            "bwd_X1": 5.5 * C + 7.5 * GE,                               # bA, gx1 -> gbA
+            "bwd_BA": 7.5 * C + 3.75 * GE,                              # x, gbA, gB, gout -> gx; GTV only
             "bwd_weights": 2.5 * (2 * C + 2 * GE),
-            "gw_X3": 2 * C + 1.25 * GE + 2.5 * GE,                      # x2, gout, wT -> gwL, gwT
-            "gw_X2": 3 * C + 1.25 * GE + 5 * GE,                        # x1, gout, gx2, wT, gw -> gw
-            "gw_X1": 2 * C + 1.25 * GE + 5 * GE,
-            "gw_BA": 2 * C + 1.25 * GE + 2.5 * GE,                      # y, gbA, wT, gwT -> gwT
+            "proj_fwd": 7 * C,      # x -> feat0 (3C); space-to-depth (2C); 2x2-s2 conv (1.25C); 1x1 at half resolution (0.75C)
+            "proj_dgrad": 7 * C,
+            "proj_wgrad": 5 * C,    # (gfeat0, x) 3C; (gxd, s2d x) 1.25C; (gfeat1, xd) 0.75C
+            "gw": 0.0,              # the round-1 gradient pass: not launched by the default backward
         }[slot]
         total += per_px * N * 4
     return total
@@ -209,6 +216,52 @@ def measured_peaks():
     if os.path.exists(p):
         return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ 4K inference (config 4)
+def infer4k(blocks, dev, rank, world, steps=3, warmup=2):
+    """BASELINE config[3]: the four filter blocks, forward only, on the feature maps of ONE 3840x2160 image
+    ([1,48,2160,3840] ... [1,384,270,480]); with N ranks every map is cut into N row strips and the blocks run stage by stage
+    with one 8-row NCCL halo exchange per solver stage, batched over the scales (shard.sharded_filtering_staged): STRONG scaling,
+    results identical to the single-GPU run (tests/test_shard_cpu.py, tests/multi_gpu_check.py)."""
+    import torch
+    import torch.distributed as dist
+    from imagerestoration_development_unrolling_b200 import shard
+    H0, W0 = 2160, 3840
+    strips = []
+    for s, d in enumerate(DIMS):
+        a, b = shard.strip_bounds(H0 >> s, world, align=2)[rank]
+        strips.append(torch.randn(1, d, b - a, W0 >> s, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + s)))
+
+    def run():
+        with torch.no_grad():
+            return shard.sharded_filtering_staged(blocks, strips, rank, world)
+
+    for _ in range(warmup):
+        run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    del strips
+    torch.cuda.empty_cache()
+    return {"metric": "infer_Mpix_per_s", "value": H0 * W0 / ms / 1e3, "unit": "Mpix/s", "ms_per_image": ms, "n_gpus": world,
+            "scaling": "strong", "steps": steps, "warmup": warmup,
+            "workload": "v13 four LocalLowpassFilteringBlock, forward, feature maps of one 3840x2160 image, row strips, one 8-row "
+                        "halo exchange per solver stage batched over the scales",
+            "compulsory_GBs": sum(8 * C * (H0 >> s) * (W0 >> s) for s, C in enumerate(DIMS)) / (ms / 1e3) / 1e9}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -341,6 +394,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
 
+    i4k = None if a.no_infer4k else infer4k(blocks, dev, rank, world)
+
     if rank == 0:
         pix = B * RES * RES * world
         value = pix * a.steps / (ms / 1e3) / 1e6
@@ -354,7 +409,7 @@ def main():
         whole_ms = sum(v[0] for v in per_slot.values()) / a.steps
         # DRAM bytes of the same kernels from the committed ncu capture of one step at these sizes (profiles/, tools/ncu_slots.py)
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_step_slots.json")
+        tp = os.path.join(ROOT, "profiles", "r02_step_slots.json")
         if os.path.exists(tp) and B == BATCH:
             traffic = json.load(open(tp))["slots"].get(top, {}).get("dram_bytes")
         per_kernel = {}
@@ -364,8 +419,9 @@ def main():
         roofline = {
             "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": peak_src, "traffic": traffic,
-            "note": "a slot = the launches of one solver stage over the four scales (bwd_X2 = parts A and B); achieved = "
-                    "algorithmic bytes of the slot / its summed CUDA-event time inside the timed region",
+            "note": "a slot = the launches of one solver stage over the four scales (backward stages: a half- and a full-resolution "
+                    "launch each, edge-weight gradients included; bwd_X2 = parts A and B); achieved = algorithmic bytes of the "
+                    "slot / its summed CUDA-event time inside the timed region",
             "per_kernel": per_kernel,
             "kernel_share_of_step": round(top_ms_per_step / (ms / a.steps), 4),
             "own_kernels_share_of_step": round(whole_ms / (ms / a.steps), 4),
@@ -383,6 +439,8 @@ def main():
                     "note": "pinned-host inputs of step i+1 are copied on a side stream while step i computes"},
             "roofline": roofline,
         }
+        if i4k is not None:
+            line["infer4k"] = i4k
         if world == 1 and not a.no_cpu_baseline:
             mpix, dt, cores, kind = run_cpu(steps=3, warmup=1)
             line["cpu_baseline"] = {"value": mpix, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_text(kind, cores, 3)}

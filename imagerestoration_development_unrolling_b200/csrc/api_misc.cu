@@ -266,7 +266,9 @@ extern "C" int glrgtv_space_to_depth(int inverse, long planes, int H, int W, con
     if (!x || !y || (((uintptr_t)x | (uintptr_t)y) & 15u)) return GLRGTV_ERR_POINTER;
     const long total = planes * (H / 2) * (W / 8);
     const long blocks = (total + 255) / 256;
+    GLR_PROF_BEGIN(inverse ? GLRGTV_SLOT_PROJ_DGRAD : GLRGTV_SLOT_PROJ_FWD, stream);
     GLR_LAUNCH(k_space_to_depth, dim3((unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks)), 256, 0, stream, x, y, planes, H, W, inverse);
+    GLR_PROF_END(inverse ? GLRGTV_SLOT_PROJ_DGRAD : GLRGTV_SLOT_PROJ_FWD, stream);
     return GLR_CHECK_LAUNCH();
 }
 #endif

@@ -866,24 +866,24 @@ extern "C" int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params
         b.z = sv->x2; b.src0 = gout; b.src1 = nullptr; b.op0 = sv->r1; b.op1 = sv->bB; b.op2 = x; b.out = gx2;
         if ((rc = glr_stream_bwd_stage<BW_X3>(b, GLRGTV_SLOT_BWD_X3, stream))) return rc;
         w.z = sv->x2; w.src0 = gout; w.src1 = nullptr; w.assign = 1;
-        if ((rc = gw_stage<BW_X3>(w, GLRGTV_SLOT_GW_X3, stream))) return rc;
+        if ((rc = gw_stage<BW_X3>(w, GLRGTV_SLOT_GW, stream))) return rc;
         // X2: through x2 = x1 + a1 r1, r1 = bB - A x1 (part A) and bB = y + R_thr x1 (part B)
         b.z = sv->x1; b.src0 = gout; b.src1 = gx2; b.op0 = sv->r1; b.op1 = nullptr; b.op2 = nullptr; b.out = gx1;
         if ((rc = glr_stream_bwd_stage<BW_X2A>(b, GLRGTV_SLOT_BWD_X2, stream))) return rc;
         b.op0 = gx1;
         if ((rc = glr_stream_bwd_stage<BW_X2B>(b, GLRGTV_SLOT_BWD_X2, stream))) return rc;
         w.z = sv->x1; w.src0 = gout; w.src1 = gx2; w.assign = 0;
-        if ((rc = gw_stage<BW_X2A>(w, GLRGTV_SLOT_GW_X2, stream))) return rc;      // both parts of X2 in one pass
+        if ((rc = gw_stage<BW_X2A>(w, GLRGTV_SLOT_GW, stream))) return rc;      // both parts of X2 in one pass
         // X1: through x1 = bA + a0 (bA - A bA)
         b.z = sv->bA; b.src0 = gx1; b.src1 = nullptr; b.op0 = nullptr; b.out = gbA;
         if ((rc = glr_stream_bwd_stage<BW_X1>(b, GLRGTV_SLOT_BWD_X1, stream))) return rc;
         w.z = sv->bA; w.src0 = gx1; w.src1 = nullptr;
-        if ((rc = gw_stage<BW_X1>(w, GLRGTV_SLOT_GW_X1, stream))) return rc;
+        if ((rc = gw_stage<BW_X1>(w, GLRGTV_SLOT_GW, stream))) return rc;
         // BA: through bA = y + R_lin y, plus the pointwise paths into y (bB, skip)
         b.z = x; b.src0 = gbA; b.op0 = gout; b.op1 = gx2; b.out = gx;
         if ((rc = glr_stream_bwd_stage<BW_BA>(b, GLRGTV_SLOT_BWD_BA, stream))) return rc;
         w.z = x; w.src0 = gbA;
-        if ((rc = gw_stage<BW_BA>(w, GLRGTV_SLOT_GW_BA, stream))) return rc;
+        if ((rc = gw_stage<BW_BA>(w, GLRGTV_SLOT_GW, stream))) return rc;
         glrgtv_shape sc = *s;
         sc.H /= 2; sc.W /= 2;
         GLR_PROF_BEGIN(GLRGTV_SLOT_BWD_WEIGHTS, stream);

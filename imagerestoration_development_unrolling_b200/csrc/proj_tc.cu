@@ -372,7 +372,7 @@ int pt_sms() {
     return sms[dev] > 0 ? sms[dev] : 148;
 }
 template <int MODE>
-int pt_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ProjTcArgs& a, cudaStream_t st) {
+int pt_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ProjTcArgs& a, int slot, cudaStream_t st) {
     PtSmem lay; lay.NC = a.NC; lay.stages = 1;
     int S = (int)((220 * 1024 - 2048) / lay.stage_bytes());
     if (S > 6) S = 6;
@@ -383,6 +383,7 @@ int pt_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ProjTcArgs& a, cud
     const long grid = a.units < pt_sms() ? a.units : pt_sms();
     ++g_glr_launches;
     k_proj_tc<MODE><<<(unsigned)grid, PT_THREADS, lay.total(), st>>>(tmA, tmB, a);
+    GLR_PROF_END(slot, st);
     return GLR_CHECK_LAUNCH();
 }
 }  // namespace
@@ -400,6 +401,8 @@ extern "C" int glrgtv_proj_gemm(int transpose_w, int batch, int M, int N, int K,
     if (workspace_bytes < glrgtv_proj_gemm_workspace_bytes(M, K)) return GLRGTV_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     float* Wp = (float*)workspace;
+    const int slot = transpose_w ? GLRGTV_SLOT_PROJ_DGRAD : GLRGTV_SLOT_PROJ_FWD;
+    GLR_PROF_BEGIN(slot, st);
     ++g_glr_launches;
     k_proj_wprep<<<(nout * kred + 255) / 256 < 1024 ? (nout * kred + 255) / 256 : 1024, 256, 0, st>>>(W, Wp, nout, kred, transpose_w);
     ProjTcArgs a = {};
@@ -410,7 +413,7 @@ extern "C" int glrgtv_proj_gemm(int transpose_w, int batch, int M, int N, int K,
     CUtensorMap tmA, tmB;
     if (int rc = pt_map(&tmA, X, N, kred, batch, PT_STAGE_K, true)) return rc;
     if (int rc = pt_map(&tmB, Wp, kred, nout, 2, a.NC)) return rc;
-    return pt_launch<0>(tmA, tmB, a, st);
+    return pt_launch<0>(tmA, tmB, a, slot, st);
 }
 
 // gW [M,K] += sum_b gY[b] (M x N) . X[b]^T (N x K)     (ACCUMULATES: the caller zeroes gW)
@@ -433,7 +436,8 @@ extern "C" int glrgtv_proj_wgrad(int batch, int M, int N, int K, const float* gY
     CUtensorMap tmA, tmB;
     if (int rc = pt_map(&tmA, gY, N, M, batch, 128)) return rc;
     if (int rc = pt_map(&tmB, X, N, K, batch, a.NC)) return rc;
-    return pt_launch<1>(tmA, tmB, a, (cudaStream_t)stream);
+    GLR_PROF_BEGIN(GLRGTV_SLOT_PROJ_WGRAD, stream);
+    return pt_launch<1>(tmA, tmB, a, GLRGTV_SLOT_PROJ_WGRAD, (cudaStream_t)stream);
 }
 
 #else

@@ -22,32 +22,31 @@ STAGE_HALO_ROWS = 8     # reach of ONE solver stage: 3 rows at full resolution, 
 # ----------------------------------------------------------------------------------------------- training
 def allreduce_gradients(params: Sequence[torch.nn.Parameter], group=None, average: bool = True,
                         flat: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Sum (or average) the gradients of `params` across ranks with one all-reduce of a flat buffer and write the
-    result back into each `.grad`.  Parameters without a gradient contribute zeros.  Returns the flat buffer."""
+    """Sum (or average) the gradients of `params` across ranks with ONE all-reduce of a flat buffer; afterwards every `.grad`
+    is a VIEW of that buffer (no copy back).  Packing is one fused multi-tensor copy (torch._foreach_copy_), not one launch per
+    parameter: the four filter blocks have 128 small parameter tensors and the step is only ~35 ms.  Parameters without a
+    gradient contribute zeros.  Returns the flat buffer (pass it back in as `flat` to reuse the allocation)."""
     params = [p for p in params if p.requires_grad]
     n = sum(p.numel() for p in params)
     if flat is None or flat.numel() != n:
         flat = torch.empty(n, dtype=params[0].dtype, device=params[0].device)
-    o = 0
+    views, o = [], 0
     for p in params:
-        seg = flat[o:o + p.numel()]
-        if p.grad is None:
-            seg.zero_()
-        else:
-            seg.copy_(p.grad.reshape(-1))
+        views.append(flat[o:o + p.numel()].view_as(p))
         o += p.numel()
+    have = [(v, p.grad) for v, p in zip(views, params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+    if len(have) < len(params):
+        for v, p in zip(views, params):
+            if p.grad is None:
+                v.zero_()
+    if have:
+        torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, group=group)
         if average:
             flat.div_(dist.get_world_size(group))
-    o = 0
-    for p in params:
-        g = flat[o:o + p.numel()].view_as(p)
-        if p.grad is None:
-            p.grad = g.clone()
-        else:
-            p.grad.copy_(g)
-        o += p.numel()
+    for v, p in zip(views, params):
+        p.grad = v
     return flat
 
 
@@ -288,7 +287,9 @@ class ShardedMultiScaleFilter:
         kern = self.cnn_kernels
         if isinstance(kern, str):
             from . import host_cnn
-            kern = host_cnn.CudaCnnKernels() if (x.is_cuda and not torch.is_grad_enabled()) else None
+            # libglrgtv's pixel_rstd / dwconv_gate take rows of whole 16-byte pieces (W % 4 == 0), the guard LocalNonLinearBlock.forward
+            # applies too: e.g. a 336x496 CBSD68 image is 42 columns wide at the 1/8 scale and stays on the module path there
+            kern = host_cnn.CudaCnnKernels() if (x.is_cuda and not torch.is_grad_enabled() and x.shape[-1] % 4 == 0) else None
         if kern is not None:
             from . import host_cnn
             ex = (lambda first, last: exchange_rows(first, last, self.rank, self.world, self.group)) if self.world > 1 else None
@@ -326,8 +327,23 @@ class ShardedMultiScaleFilter:
         if self.block_forward is not None:
             return tuple(self.block_forward(blk, c, i) for i, (blk, c) in enumerate(zip(blocks, strips)))
         runners = [self.stage_runner(blk) for blk in blocks] if self.stage_runner is not None else None
+        # the per-stage exchange runs on the streaming stage kernels (W % 8 == 0 at every scale, i.e. W % 64 == 0 at the input) and
+        # needs strips of at least two 8-row halos; other geometries - the same on every rank, so no rank is left waiting in an
+        # exchange - take one 26-row halo exchange per block, which works with any block implementation
+        staged = runners is not None or all(c.shape[-1] % 8 == 0 for c in strips)
+        if self.world > 1:
+            # strip heights differ between ranks: agree on the path (and on failing) BEFORE any exchange, so that no rank raises
+            # alone and leaves its neighbours waiting
+            thin = torch.tensor([int(any(c.shape[-2] < 2 * STAGE_HALO_ROWS for c in strips)),
+                                 int(any(c.shape[-2] < BLOCK_HALO_ROWS for c in strips))], device=strips[0].device)
+            dist.all_reduce(thin, op=dist.ReduceOp.MAX, group=self.group)
+            staged = staged and int(thin[0].item()) == 0
+            if not staged and int(thin[1].item()):
+                raise ValueError(f"some rank's strip is thinner than the {BLOCK_HALO_ROWS}-row halo of a filter block: use fewer ranks")
         with torch.no_grad():
-            return tuple(sharded_filtering_staged(blocks, strips, self.rank, self.world, self.group, runners))
+            if staged:
+                return tuple(sharded_filtering_staged(blocks, strips, self.rank, self.world, self.group, runners))
+            return tuple(sharded_block_forward(blk, c, self.rank, self.world, group=self.group) for blk, c in zip(blocks, strips))
 
     def decode(self, coefs):
         m = self.model

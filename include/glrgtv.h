@@ -82,8 +82,10 @@ typedef enum glrgtv_prof_slot {
     GLRGTV_SLOT_FWD_BA = 1, GLRGTV_SLOT_FWD_X1 = 2, GLRGTV_SLOT_FWD_X2 = 3, GLRGTV_SLOT_FWD_X3 = 4,
     GLRGTV_SLOT_BWD_X3 = 5, GLRGTV_SLOT_BWD_X2 = 6, GLRGTV_SLOT_BWD_X1 = 7, GLRGTV_SLOT_BWD_BA = 8,
     GLRGTV_SLOT_BWD_WEIGHTS = 9,
-    /* edge-weight gradient kernels of the streaming backward (block_gw.cu), one per stage (X2 = both parts) */
-    GLRGTV_SLOT_GW_X3 = 10, GLRGTV_SLOT_GW_X2 = 11, GLRGTV_SLOT_GW_X1 = 12, GLRGTV_SLOT_GW_BA = 13,
+    /* the feature projections (csrc/proj_tc.cu + the space-to-depth copy): forward, input gradient, weight gradient */
+    GLRGTV_SLOT_PROJ_FWD = 10, GLRGTV_SLOT_PROJ_DGRAD = 11, GLRGTV_SLOT_PROJ_WGRAD = 12,
+    /* edge-weight gradient pass of the ROUND-1 backward (block_gw.cu; the default backward folds it into the stages) */
+    GLRGTV_SLOT_GW = 13,
     GLRGTV_SLOT_COUNT = 14
 } glrgtv_prof_slot;
 int glrgtv_profile_enable(int on);

@@ -58,3 +58,28 @@ def test_compiled_block_matches_eager():
     out2 = cblk(x2)
     gx2, = torch.autograd.grad(out2, x2, g)
     assert rel(out2, out) < 1e-6 and rel(gx2, gx) < 1e-5
+
+
+@pytest.mark.gpu
+def test_png_crop_psnr_within_0p01_db_of_the_reference(golden_dir):
+    """The evaluation pipeline on the device (evalpipe.restore_image / psnr_255: reflect-pad to 16, model, crop, clamp,
+    img_as_ubyte, PSNR) on a real-image crop of the reference's 0020.png with sigma = 25 noise from RandomState(2204), against
+    the reference model run through the reference's own evaluation steps in fp64 (tests/golden/make_golden_png.py)."""
+    from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
+    from imagerestoration_development_unrolling_b200 import evalpipe
+    z = _load(golden_dir)
+    g = np.load(os.path.join(golden_dir, "png_crop_0020.npz"))
+    m = M.AbtractMultiScaleGraphFilter(**CFG)
+    m.load_state_dict({str(k): torch.from_numpy(z["sd." + str(k)]) for k in z["keys"]}, strict=True)
+    m = m.cuda().eval()
+    noisy = torch.from_numpy(g["noisy"]).permute(2, 0, 1)[None].contiguous().cuda()            # [1,3,72,104]: padded to 80x112 inside
+    clean = torch.from_numpy(g["clean_u8"].astype(np.float32)).permute(2, 0, 1)[None].cuda()
+    restored = evalpipe.restore_image(m, noisy)
+    psnr = float(evalpipe.psnr_255(restored, clean))
+    assert abs(psnr - float(g["psnr"])) < 0.01, (psnr, float(g["psnr"]))
+    ref_u8 = torch.from_numpy(g["out_u8"].astype(np.float32)).permute(2, 0, 1)[None].cuda()
+    diff = (restored - ref_u8).abs()
+    assert float(diff.max()) <= 1.0 and float((diff > 0).float().mean()) < 0.02      # quantisation ties only
+    # the sharded executor gives the same image (its W % 4 / thin-strip guards fall back to the module path)
+    restored2 = evalpipe.restore_image(evalpipe.inference_executor(m), noisy)
+    assert float((restored2 - restored).abs().max()) <= 1.0
