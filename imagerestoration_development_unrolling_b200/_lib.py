@@ -50,7 +50,7 @@ class BlockGrads(C.Structure):
 
 
 class BlockSaved(C.Structure):
-    _fields_ = [(n, fp) for n in ("wT0", "wL0", "wT1", "wL1", "bA", "x1", "bB", "r1", "x2", "cT0", "cT1")]
+    _fields_ = [(n, fp) for n in ("wT0", "wL0", "wT1", "wL1", "bA", "x1", "bB", "r1", "x2", "cT0", "cT1", "vc")]
 
 
 def make_window(edges) -> Window:
@@ -75,6 +75,7 @@ _SIGS = {
     "glrgtv_set_stream_loader": (C.c_int, [C.c_int]),
     "glrgtv_stream_launch_count": (C.c_ulonglong, []),
     "glrgtv_set_bwd_kernels": (C.c_int, [C.c_int]),
+    "glrgtv_set_fwd_kernels": (C.c_int, [C.c_int]),
     "glrgtv_profile_read": (C.c_int, [_P(C.c_float), _P(C.c_int), C.c_int]),
     "glrgtv_edge_weights_fwd": (C.c_int, [_P(Shape), _P(Window), fp, fp, fp, fp]),
     "glrgtv_edge_weights_bwd": (C.c_int, [_P(Shape), _P(Window), fp, fp, fp, fp, fp, fp, fp, fp]),

@@ -13,6 +13,7 @@
 // into column strips of STREAM_STRIP valid columns with 8 halo columns per side - the reach of the chain through the
 // half-resolution branch - whose edge lanes compute throw-away values.  Other widths take the plane kernels of block_fwd.cu.
 #include "stream.cuh"
+#include "fw2.cuh"
 
 enum { MODE_BA = 0, MODE_X1 = 1, MODE_X2 = 2, MODE_X3 = 3 };
 enum { PL_Z = 0, PL_SA = 1, PL_SB = 2, PL_LA = 3, PL_OB = 4, PL_OT = 5, PL_COUNT = 6 };
@@ -27,6 +28,7 @@ struct StreamFwdArgs {
     const float* r1_in;  // X3
     const float *wT0, *wL0, *wT1, *wL1;
     const float *cT0, *cT1;   // symmetric GTV coefficients [B,G,2,H,W] / [B,G,2,H/2,W/2]
+    float* vc;                // scratch of the second-generation kernels (fw2.cuh), or NULL
     float* out0;  // BA: bA | X1: x1 | X2: x2 | X3: out
     float* out1;  // X2: bB
     float* out2;  // X2: r1
@@ -711,9 +713,36 @@ static int launch_stream_kernel(const StreamFwdArgs& a, const StreamPlan& p, lon
     GLR_LAUNCH_FIBERS((k_stream_fwd<MODE, XW, TMA>), dim3((unsigned)blocks), p.threads, smem, stream, a);
     return GLRGTV_OK;
 }
+// second-generation pair walkers (fw2.cuh; instantiated in fw2_<stage>.cu)
+extern int g_glr_fw2;
+bool glr_fw2_eligible(const glrgtv_shape* s);
+extern template int glr_fw2_stage<FW_BA>(F2Args, const float*, const float*, const float*, float*, int, int, void*);
+extern template int glr_fw2_stage<FW_X1>(F2Args, const float*, const float*, const float*, float*, int, int, void*);
+extern template int glr_fw2_stage<FW_X2>(F2Args, const float*, const float*, const float*, float*, int, int, void*);
+extern template int glr_fw2_stage<FW_X3>(F2Args, const float*, const float*, const float*, float*, int, int, void*);
+static int glr_fw2_dispatch(int mode, const StreamFwdArgs& a, void* stream) {
+    F2Args f = {};
+    f.s = a.s; f.p = a.p;
+    f.z = a.z; f.cT = a.cT0; f.wT = a.wT0; f.wL = a.wL0;
+    f.out0 = a.out0; f.out1 = a.out1; f.out2 = a.out2;
+    switch (mode) {
+        case MODE_BA: return glr_fw2_stage<FW_BA>(f, a.cT1, a.wT1, a.wL1, a.vc, a.row_base, a.row_end, stream);
+        case MODE_X1: return glr_fw2_stage<FW_X1>(f, a.cT1, a.wT1, a.wL1, a.vc, a.row_base, a.row_end, stream);
+        case MODE_X2: f.op0 = a.y; return glr_fw2_stage<FW_X2>(f, a.cT1, a.wT1, a.wL1, a.vc, a.row_base, a.row_end, stream);
+        default: f.op0 = a.bB_in; f.op1 = a.r1_in; f.op2 = a.p.skip ? a.y : nullptr;
+                 return glr_fw2_stage<FW_X3>(f, a.cT1, a.wT1, a.wL1, a.vc, a.row_base, a.row_end, stream);
+    }
+}
+
 template <int MODE>
 static int launch_stream_stage(StreamFwdArgs a, void* stream) {
     const glrgtv_shape& s = a.s;
+    if (g_glr_fw2 && a.vc != nullptr && glr_fw2_eligible(&s)) {
+        GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_BA + MODE, stream);
+        const int rc2 = glr_fw2_dispatch(MODE, a, stream);
+        GLR_PROF_END(GLRGTV_SLOT_FWD_BA + MODE, stream);
+        return rc2;
+    }
     const StreamPlan p = stream_plan(s, a.row_end - a.row_base);
     a.nch = p.nch; a.band_rows = p.band_rows; a.n_bands = p.n_bands; a.n_strips = p.n_strips;
     const long blocks = (long)s.B * s.G * (s.F / p.nch) * p.n_bands * p.n_strips;
@@ -749,7 +778,7 @@ int glr_stream_block_fwd(const glrgtv_shape* s, const glrgtv_block_params* p, co
     int rc;
     StreamFwdArgs a;
     a.s = *s; a.p = *p;
-    a.wT0 = sv->wT0; a.wL0 = sv->wL0; a.wT1 = sv->wT1; a.wL1 = sv->wL1; a.cT0 = sv->cT0; a.cT1 = sv->cT1;
+    a.wT0 = sv->wT0; a.wL0 = sv->wL0; a.wT1 = sv->wT1; a.wL1 = sv->wL1; a.cT0 = sv->cT0; a.cT1 = sv->cT1; a.vc = sv->vc;
     a.y = nullptr; a.bB_in = nullptr; a.r1_in = nullptr; a.out1 = nullptr; a.out2 = nullptr;
     a.nch = 1; a.band_rows = s->H; a.n_bands = 1; a.n_strips = 1; a.row_base = 0; a.row_end = s->H;
     a.z = x; a.out0 = sv->bA;
@@ -769,7 +798,7 @@ int glr_stream_block_fwd_stage(int stage, const glrgtv_shape* s, const glrgtv_bl
                                const glrgtv_block_saved* sv, int row0, int row1, void* stream) {
     StreamFwdArgs a;
     a.s = *s; a.p = *p;
-    a.wT0 = sv->wT0; a.wL0 = sv->wL0; a.wT1 = sv->wT1; a.wL1 = sv->wL1; a.cT0 = sv->cT0; a.cT1 = sv->cT1;
+    a.wT0 = sv->wT0; a.wL0 = sv->wL0; a.wT1 = sv->wT1; a.wL1 = sv->wL1; a.cT0 = sv->cT0; a.cT1 = sv->cT1; a.vc = sv->vc;
     a.y = nullptr; a.bB_in = nullptr; a.r1_in = nullptr; a.out1 = nullptr; a.out2 = nullptr;
     a.nch = 1; a.band_rows = s->H; a.n_bands = 1; a.n_strips = 1; a.row_base = row0; a.row_end = row1;
     switch (stage) {

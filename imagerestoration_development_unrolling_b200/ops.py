@@ -537,7 +537,7 @@ space_to_depth.register_autograd(lambda ctx, g: (space_to_depth(g, not ctx.inver
 # params layout: for each of GTVmodule00, GLRmodule00, GTVmodule01, GLRmodule01: p01, p02a, p02b, p03, multiM (20),
 # then alphaCGD, betaCGD, muys00, ro00, gamma00, muys01, ro01, gamma01 (8), then optionally skip_weight (1).
 _N_BLOCK_PARAMS = 28
-_SAVED = ("wT0", "wL0", "wT1", "wL1", "bA", "x1", "bB", "r1", "x2", "cT0", "cT1")
+_SAVED = ("wT0", "wL0", "wT1", "wL1", "bA", "x1", "bB", "r1", "x2", "cT0", "cT1", "vc")
 
 
 def _block_structs(params: Sequence[Tensor]):
@@ -561,7 +561,7 @@ def _block_geometry(x: Tensor, n_graphs: int):
 
 def _saved_shapes(B, G, F, H, W):
     return ([(B, G, 4, H, W)] * 2 + [(B, G, 4, H // 2, W // 2)] * 2 + [(B, G, F, H, W)] * 5 +
-            [(B, G, 2, H, W), (B, G, 2, H // 2, W // 2)])
+            [(B, G, 2, H, W), (B, G, 2, H // 2, W // 2), (2, B, G, F, H // 2, W // 2)])
 
 
 @torch.library.custom_op(f"{_NS}::lowpass_block_fwd", mutates_args=())

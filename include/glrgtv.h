@@ -203,6 +203,9 @@ typedef struct glrgtv_block_saved {
     float *wT0, *wL0, *wT1, *wL1;
     float *bA, *x1, *bB, *r1, *x2;
     float *cT0, *cT1;
+    /* scratch of the second-generation forward stage kernels (csrc/fw2.cuh): the half-resolution launches' results,
+     * [2][B,G,F,H/2,W/2]; NULL => the round-1 forward kernels run */
+    float* vc;
 } glrgtv_block_saved;
 
 /* Which kernels the fused block entry points use: 0 = automatic (register-streaming kernels when W % 8 == 0, planes
@@ -216,6 +219,10 @@ int glrgtv_set_stream_loader(int mode);
  * into the adjoint walk; W % 4 == 0, all channels of a graph in one CTA), 1 = the round-1 walkers + separate gradient pass.
  * Same results; a test / comparison switch. */
 int glrgtv_set_bwd_kernels(int generation);
+/* Forward stage kernels: 1 (default) = the round-1 walkers of csrc/block_stream_fwd.cu, 2 = the pair walkers of
+ * csrc/fw2.cuh (W % 8 == 0, any width in column strips; need the scratch glrgtv_block_saved.vc).  Same results; the
+ * pair walkers measured no faster on a B200 (profiles/r02_summary.md) and stay a tested opt-in. */
+int glrgtv_set_fwd_kernels(int generation);
 /* streaming-path kernels launched since the library was loaded (diagnostic: lets a test assert which path ran) */
 unsigned long long glrgtv_stream_launch_count(void);
 

@@ -25,13 +25,32 @@ def stream_path(request):
 
 
 # planes wider than one 64-lane walker are cut into column strips (forward only): 2 and 3 strips, ragged last strip
-WIDE = [(6, 1, 1, 8, 272), (4, 2, 1, 6, 504), (2, 1, 1, 4, 488)]
+WIDE = [(6, 1, 1, 8, 272), (4, 2, 1, 6, 504), (2, 1, 1, 4, 488), (6, 1, 1, 6, 504), (12, 1, 1, 4, 520)]
 
 
+def fw2_eligible(F, H, W):
+    """mirror of glr_fw2_eligible (csrc/fw2.cu): W % 8 == 0; a CTA of <= 384 threads holds at least half of a graph's channels on a
+    window of >= 16 columns at both resolutions (wider planes: column strips)"""
+    if W % 8 or H % 2 or W < 16 or H < 4:
+        return False
+    for lw in (W, W // 2):
+        lanes = 4
+        while 2 * lanes < lw:
+            lanes *= 2
+        nch = lambda L: max([n for n in range(1, F + 1) if F % n == 0 and n * L <= 384], default=0)
+        while lanes > 4 and nch(lanes) * 2 < F:
+            lanes //= 2
+        if lanes < 8 or nch(lanes) < 1 or 6 * nch(lanes) < 10:
+            return False
+    return True
+
+
+@pytest.mark.parametrize("generation", [1, 2], ids=["round1", "fw2"])
 @pytest.mark.parametrize("case", CASES + WIDE)
-def test_stream_block_forward(case):
+def test_stream_block_forward(case, generation):
     dim, G, B, H, W = case
     F = dim // G
+    E.emu_lib().glrgtv_set_fwd_kernels(generation)
     sd = random_block_state(dim, G, seed=300 + H)
     x = torch.randn(B, dim, H, W, generator=torch.Generator().manual_seed(H * W))
     ref_out, inter = O.mixture_gtvglr_forward({k: v.double() for k, v in sd.items()}, x.double(), "local_filter.",
@@ -42,7 +61,12 @@ def test_stream_block_forward(case):
     p, keep = block_structs(sd)
     sv, saved = alloc_saved(B, G, F, H, W)
     out = torch.empty_like(x)
+    n0 = E.emu_lib().glrgtv_stream_launch_count()
     E.call("glrgtv_block_fwd", L.make_shape(B, G, F, H, W), p, x, f0, f1, out, sv, None)
+    nl = E.emu_lib().glrgtv_stream_launch_count() - n0
+    E.emu_lib().glrgtv_set_fwd_kernels(1)
+    # round 1: one launch per stage; fw2: a half-resolution and a full-resolution launch per stage
+    assert nl == (8 if generation == 2 and fw2_eligible(F, H, W) else 4), nl
     for n in ("wT0", "wL0", "wT1", "wL1"):
         assert rel(saved[n], inter[n]) < 5e-6, n
     for n in ("bA", "x1", "bB", "r1", "x2"):

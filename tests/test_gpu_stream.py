@@ -25,6 +25,7 @@ def lib():
     lib.glrgtv_set_block_path(0)
     lib.glrgtv_set_stream_loader(0)
     lib.glrgtv_set_bwd_kernels(2)
+    lib.glrgtv_set_fwd_kernels(1)
 
 
 # every walker width (8 / 16 / 32 / 64 lanes), partial walkers, F = 6 and 12, several channels per CTA
@@ -34,11 +35,14 @@ CASES = [(48, 8, 2, 32, 256), (96, 16, 1, 20, 128), (24, 2, 1, 36, 72), (192, 16
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("loader", [1, 2, 3], ids=["cp_async", "tma", "round1_bwd"])
+@pytest.mark.parametrize("loader", [1, 2, 3, 4], ids=["cp_async", "tma", "round1_bwd", "fw2_fwd"])
 def test_streaming_path_against_oracle(M, lib, case, loader):
     dim, G, B, H, W = case
-    if loader == 3:                         # the round-1 backward kernels (block_stream_bwd.cu + block_gw.cu) stay a tested path
+    if loader == 3:                         # the round-1 kernels (block_stream_fwd / bwd.cu + block_gw.cu) stay a tested path
         lib.glrgtv_set_bwd_kernels(1)
+        loader = 1
+    if loader == 4:                         # the opt-in forward pair walkers (csrc/fw2.cuh)
+        lib.glrgtv_set_fwd_kernels(2)
         loader = 1
     sd = random_block_state(dim, G, seed=dim + H + W)
     gen = torch.Generator().manual_seed(3 * H + W)
@@ -50,7 +54,8 @@ def test_streaming_path_against_oracle(M, lib, case, loader):
     out, gx, pg = run_block(make_block(M, dim, G, sd), x, gout)
     # 4 forward stages; backward: 5 stages x (half + full resolution) with the pair walkers of csrc/bw2.cu (edge-weight gradients
     # folded in), or 5 stages + 8 gradient kernels with the round-1 kernels (shapes the pair walkers do not take)
-    assert lib.glrgtv_stream_launch_count() - n0 in (4 + 10, 4 + 13)
+    # (forward: a half- and a full-resolution launch per stage with csrc/fw2.cuh, one launch per stage with the round-1 kernels)
+    assert lib.glrgtv_stream_launch_count() - n0 in (8 + 10, 8 + 13, 4 + 10, 4 + 13)
     check_against(out, gx, pg, *ref)
 
 
@@ -90,6 +95,8 @@ def test_wide_planes(M, lib):
     lib.glrgtv_set_block_path(2)
     n0 = lib.glrgtv_stream_launch_count()
     out, gx, pg = run_block(make_block(M, dim, G, sd), x, gout)
+    # forward: csrc/fw2.cuh in column strips (8 launches); backward: the round-1 kernels in column strips (5 + 8: the pair
+    # walkers of csrc/bw2.cuh take planes of up to 256 columns)
     assert lib.glrgtv_stream_launch_count() - n0 == 4 + 13
     check_against(out, gx, pg, *ref)
 
@@ -224,3 +231,36 @@ def test_pair_walkers_equal_round1_kernels_at_benchmark_size(M, lib, scale):
     for k in pg1:
         if float(pg1[k].abs().max()) > 0:
             assert rel(pg2[k], pg1[k]) < 2e-4, (k, rel(pg2[k], pg1[k]))
+
+
+@pytest.mark.parametrize("scale", [0, 1, 2, 3])
+def test_forward_pair_walkers_equal_round1_kernels_at_benchmark_size(M, lib, scale):
+    """csrc/fw2.cuh against the round-1 forward kernels at the benchmark's plane sizes (compile-time geometry kernels)"""
+    dim, G = [48, 96, 192, 384][scale], [8, 16, 16, 32][scale]
+    B, H = 2, 256 >> scale
+    sd = random_block_state(dim, G, seed=31 + scale)
+    x = torch.randn(B, dim, H, H, generator=torch.Generator().manual_seed(scale)).cuda()
+    blk = make_block(M, dim, G, sd)
+    with torch.no_grad():
+        lib.glrgtv_set_fwd_kernels(1)
+        out1 = blk(x)
+        lib.glrgtv_set_fwd_kernels(2)
+        n0 = lib.glrgtv_stream_launch_count()
+        out2 = blk(x)
+        assert lib.glrgtv_stream_launch_count() - n0 == 8
+    assert rel(out2, out1) < 2e-6, rel(out2, out1)
+
+
+def test_forward_pair_walkers_on_a_4k_wide_plane(M, lib):
+    """column strips of csrc/fw2.cuh: a [1,48,64,3840] plane (16 strips of 240 columns, two CTAs per graph) against the round-1 kernels"""
+    sd = random_block_state(48, 8, seed=77)
+    x = torch.randn(1, 48, 64, 3840, generator=torch.Generator().manual_seed(3)).cuda()
+    blk = make_block(M, 48, 8, sd)
+    with torch.no_grad():
+        lib.glrgtv_set_fwd_kernels(1)
+        out1 = blk(x)
+        lib.glrgtv_set_fwd_kernels(2)
+        n0 = lib.glrgtv_stream_launch_count()
+        out2 = blk(x)
+        assert lib.glrgtv_stream_launch_count() - n0 == 8
+    assert rel(out2, out1) < 2e-6, rel(out2, out1)

@@ -45,6 +45,7 @@ def alloc_saved(B, G, F, H, W, dev="cpu"):
         keep[n] = torch.empty(B, G, F, H, W, device=dev)
     keep["cT0"] = torch.empty(B, G, 2, H, W, device=dev)
     keep["cT1"] = torch.empty(B, G, 2, H // 2, W // 2, device=dev)
+    keep["vc"] = torch.empty(2, B, G, F, H // 2, W // 2, device=dev)
     for n, v in keep.items():
         setattr(sv, n, v.data_ptr())
     return sv, keep
