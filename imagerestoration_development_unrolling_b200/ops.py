@@ -46,10 +46,16 @@ def _c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_checked_devices = set()
+
+
 def _call(name: str, ref: Tensor, *args):
     global launch_count
     launch_count += 1
     with torch.cuda.device(ref.device):
+        if ref.device.index not in _checked_devices:      # first use of this device: the kernels are sm_100a only
+            L.check(_lib().glrgtv_check_device(), _lib(), f"check_device({ref.device})")
+            _checked_devices.add(ref.device.index)
         L.call(_lib(), name, *args, _stream(ref))
 
 

@@ -211,36 +211,42 @@ def train(conf: dict, device: Optional[torch.device] = None, on_step: Optional[C
     dconf = conf["datasets"]["train"]
     dataset = DATASET_TYPES[dconf.get("type", "SyntheticNoisyPatches")](**(dconf.get("dataset_args") or {}))
     bs = int((dconf.get("dataloader_args") or {}).get("batch_size", 4))
-    sampler = ResumableShardedSampler(len(dataset), bs, rank, world, start_batch=i)
+    sampler = ResumableShardedSampler(len(dataset), bs, rank, world, start_batch=i % max(len(dataset) // (bs * world), 1))
     loader = torch.utils.data.DataLoader(dataset, batch_sampler=sampler, num_workers=tc["num_workers"])
     gen = torch.Generator(device=device)
     vconf = conf["datasets"].get("val")
     val_set = DATASET_TYPES[vconf.get("type", "SyntheticNoisyPatches")](**(vconf.get("dataset_args") or {})) if vconf else None
     params = [p for p in model.parameters() if p.requires_grad]
     flat = None
-    for noisy, clean in loader:
-        if i >= tc["total_iters"]:
-            break
-        gen.manual_seed(seed + 7919 * i + rank)                      # the latent disturbance: reproducible across resumes
-        optimizer.zero_grad(set_to_none=True)
-        loss, _ = reference_loss(model, noisy.to(device), clean.to(device), tc["w_mse"], tc["w_stab"], tc["latent_sigma"], gen)
-        loss.backward()
-        if world > 1:
-            flat = shard.allreduce_gradients(params, average=True, flat=flat)
-        optimizer.step()
-        lr_scheduler.step()
-        if on_step is not None:
-            on_step(i, float(loss.detach()))
-        if rank == 0 and tc["log_every"] and i % tc["log_every"] == 0:
-            LOG.info("iter=%d loss=%.6f lr=%.3e", i, float(loss.detach()), optimizer.param_groups[0]["lr"])
-        if rank == 0 and val_set is not None and tc["validate_every"] and (i + 1) % tc["validate_every"] == 0:
-            psnr = validate(model, val_set, device)                 # rank 0 only: no collective inside (scripts_v2:253-287)
-            LOG.info("FINISH VAL - iter=%d - psnr_testing=%.4f", i, psnr)
+    if len(dataset) < bs * world:
+        raise ValueError(f"dataset of {len(dataset)} items is smaller than one global batch ({bs} x {world} ranks)")
+    while i < tc["total_iters"]:                                     # epochs: the sampler restarts from batch 0 once exhausted
+        for noisy, clean in loader:
+            if i >= tc["total_iters"]:
+                break
+            gen.manual_seed(seed + 7919 * i + rank)                      # the latent disturbance: reproducible across resumes
+            optimizer.zero_grad(set_to_none=True)
+            loss, _ = reference_loss(model, noisy.to(device), clean.to(device), tc["w_mse"], tc["w_stab"], tc["latent_sigma"], gen)
+            loss.backward()
+            if world > 1:
+                flat = shard.allreduce_gradients(params, average=True, flat=flat)
+            optimizer.step()
+            lr_scheduler.step()
             if on_step is not None:
-                on_step(i, {"psnr": psnr})
-        if rank == 0 and ((i + 1) % tc["checkpoint_every"] == 0 or i + 1 == tc["total_iters"]):
-            save_checkpoint(folder, 0, i, model, optimizer, lr_scheduler, tc["verbose_rate"])
-        i += 1
+                on_step(i, float(loss.detach()))
+            if rank == 0 and tc["log_every"] and i % tc["log_every"] == 0:
+                LOG.info("iter=%d loss=%.6f lr=%.3e", i, float(loss.detach()), optimizer.param_groups[0]["lr"])
+            if rank == 0 and val_set is not None and tc["validate_every"] and (i + 1) % tc["validate_every"] == 0:
+                psnr = validate(model, val_set, device)                 # rank 0 only: no collective inside (scripts_v2:253-287)
+                LOG.info("FINISH VAL - iter=%d - psnr_testing=%.4f", i, psnr)
+                if on_step is not None:
+                    on_step(i, {"psnr": psnr})
+            if world > 1 and val_set is not None and tc["validate_every"] and (i + 1) % tc["validate_every"] == 0:
+                dist.barrier()                                           # the other ranks wait here, not inside the next all-reduce
+            if rank == 0 and ((i + 1) % tc["checkpoint_every"] == 0 or i + 1 == tc["total_iters"]):
+                save_checkpoint(folder, 0, i, model, optimizer, lr_scheduler, tc["verbose_rate"])
+            i += 1
+        sampler.start = 0
     if world > 1:
         dist.barrier()
     return model

@@ -90,7 +90,11 @@ def test_family_a_operators_against_oracle(window):
     assert rel(glr(y.to(dev).expand(B, G, 3, H, W).contiguous(), w, deg), O.glr_forward(yG, w_ref, st(glr), edges, "reflect")) < 1e-5
 
 
-SWEEP = [("cross3", (2, 2)), ("full3", (2, 2, 2, 2)), ("small5", (2, 4)), ("full5", (2, 2, 2)), ("full7", (2, 2))]
+# depths 4 / 6 / 8 / 16 / 32 (BASELINE config 5 sweeps the iteration count to 32); the deep schedules also vary the number of
+# iterations between the ADMM passes
+SWEEP = [("cross3", (2, 2)), ("full3", (2, 2, 2, 2)), ("small5", (2, 4)), ("full5", (2, 2, 2)), ("full7", (2, 2)),
+         ("cross3", (2,) * 8), ("small5", (4, 4, 4, 4)), ("full5", (2, 6, 8)), ("cross3", (2,) * 16), ("full3", (8, 8, 8, 8)),
+         ("full7", (4, 12, 16))]
 
 
 @pytest.mark.gpu

@@ -83,3 +83,26 @@ def test_png_crop_psnr_within_0p01_db_of_the_reference(golden_dir):
     # the sharded executor gives the same image (its W % 4 / thin-strip guards fall back to the module path)
     restored2 = evalpipe.restore_image(evalpipe.inference_executor(m), noisy)
     assert float((restored2 - restored).abs().max()) <= 1.0
+    # evaluate() = the mean of psnr_255 over the image list, one host read
+    assert abs(evalpipe.evaluate(m, [noisy, noisy], [clean, clean]) - psnr) < 1e-4
+
+
+def test_executor_on_a_cbsd68_sized_image(golden_dir):
+    """CBSD68 images are 321 x 481 -> padded to 336 x 496: the 1/8-scale planes are 42 x 62 (W % 4 == 2), outside the host-CNN
+    kernels and the streaming filter kernels.  The inference executor must fall back per scale and give the module's result
+    (shard.py)."""
+    from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
+    from imagerestoration_development_unrolling_b200 import evalpipe
+    z = _load(golden_dir)
+    m = M.AbtractMultiScaleGraphFilter(**CFG)
+    m.load_state_dict({str(k): torch.from_numpy(z["sd." + str(k)]) for k in z["keys"]}, strict=True)
+    m = m.cuda().eval()
+    noisy = torch.rand(1, 3, 321, 481, generator=torch.Generator().manual_seed(68)).cuda()
+    with torch.no_grad():
+        padded = evalpipe.pad_to_factor(noisy)
+        assert padded.shape[-2:] == (336, 496)
+        ref = m(padded)
+        out = evalpipe.inference_executor(m)(padded)
+    assert rel(out, ref) < 1e-4, rel(out, ref)
+    a, b = evalpipe.restore_image(m, noisy), evalpipe.restore_image(evalpipe.inference_executor(m), noisy)
+    assert a.shape == (1, 3, 321, 481) and float((a - b).abs().max()) <= 1.0

@@ -59,6 +59,21 @@ def test_streaming_path_against_oracle(M, lib, case, loader):
     check_against(out, gx, pg, *ref)
 
 
+def test_full_resolution_plane_against_oracle(M, lib):
+    """one [1,48,256,256] plane (BASELINE config 2's scale-0 plane, compile-time geometry kernels, several row bands) forward and
+    backward against the fp64 oracle - the oracle takes about half a minute of host time here"""
+    dim, G = 48, 8
+    sd = random_block_state(dim, G, seed=5)
+    gen = torch.Generator().manual_seed(1)
+    x, gout = torch.randn(1, dim, 256, 256, generator=gen), torch.randn(1, dim, 256, 256, generator=gen)
+    ref = O.lowpass_block_fwd_bwd({k: v.double() for k, v in sd.items()}, x.double(), gout.double())
+    lib.glrgtv_set_block_path(2)
+    n0 = lib.glrgtv_stream_launch_count()
+    out, gx, pg = run_block(make_block(M, dim, G, sd), x, gout)
+    assert lib.glrgtv_stream_launch_count() - n0 == 4 + 10
+    check_against(out, gx, pg, *ref)
+
+
 @pytest.mark.parametrize("case", [(48, 8, 4, 256, 256), (96, 16, 4, 128, 128)])
 def test_streaming_equals_plane_kernels_at_benchmark_resolution(M, lib, case):
     """two independent CUDA implementations of the path (different tiling, different order of summation)"""

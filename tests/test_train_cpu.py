@@ -174,3 +174,26 @@ def test_validation_psnr_during_training(tmp_path):
             ref = torch.round(clean.permute(2, 0, 1)[None].clamp(0, 1) * 255)
             vals.append(20 * torch.log10(255.0 / torch.sqrt(torch.mean((ref - out) ** 2))))
     assert abs(float(torch.stack(vals).mean()) - psnrs[-1][1]) < 1e-4
+
+
+def test_loop_runs_epochs_until_total_iters(tmp_path):
+    """a dataset of 3 global batches trained for 8 iterations: the loop wraps around (epochs) instead of stopping silently, writes
+    the final checkpoint, and a resume in the middle of the second epoch reproduces the uninterrupted run bit for bit"""
+    conf = _conf(tmp_path / "a", total=8, every=5)
+    conf["datasets"]["train"]["dataset_args"]["max_num_patchs"] = 6
+    seen = []
+    m_full = T.train(conf, device=torch.device("cpu"), on_step=lambda i, v: seen.append(i))
+    assert seen == list(range(8))
+    last = torch.load(T.latest_checkpoint(T.checkpoints_folder(conf)), weights_only=False)
+    assert 7 in [v for v in last.values() if isinstance(v, int)]                  # the final checkpoint (iteration 7) was written
+    conf_b = _conf(tmp_path / "b", total=5, every=5)
+    conf_b["datasets"]["train"]["dataset_args"]["max_num_patchs"] = 6
+    T.train(conf_b, device=torch.device("cpu"))
+    conf_b["train"]["total_iters"] = 8
+    m_res = T.train(conf_b, device=torch.device("cpu"))
+    for a, b in zip(m_full.state_dict().values(), m_res.state_dict().values()):
+        assert torch.equal(a, b)
+    conf_c = _conf(tmp_path / "c", total=2, bs=4)
+    conf_c["datasets"]["train"]["dataset_args"]["max_num_patchs"] = 3
+    with pytest.raises(ValueError, match="smaller than one global batch"):
+        T.train(conf_c, device=torch.device("cpu"))

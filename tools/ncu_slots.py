@@ -2,10 +2,10 @@
 """Fold an ncu launch list (--csv, one row per kernel and metric) of ONE bench step into the bench's kernel slots.
 
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-        -k regex:"^k_" -s 276 -c 92 --csv --log-file gpurun_out/step.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline
-    python tools/ncu_slots.py gpurun_out/step.csv profiles/r01_step_slots.json
+        -k regex:"^k_" -s 492 -c 164 --csv --log-file gpurun_out/step.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-infer4k
+    python tools/ncu_slots.py gpurun_out/step.csv profiles/r02_step_slots.json
 
-(92 = own kernels per step at the benchmark sizes; the first 3 steps are warm-up.)  The JSON gives, per slot, the
+(164 = own k_* kernels per step at the benchmark sizes in round 2; the first 3 steps are warm-up.)  The JSON gives, per slot, the
 number of launches, the summed ncu duration and the summed DRAM bytes: bench.py reads it for `roofline.traffic`."""
 import collections
 import csv
@@ -30,6 +30,14 @@ def slot_of(name):
         return BWD[a]
     if k in ("k_gw_stage", "k_gw_quad", "k_gw_stream"):
         return GW[a]
+    if k == "k_bw2":                      # k_bw2<MODE, COARSE, ...>: X3, X2A, X2B, X1, BA
+        return BWD[a]
+    if k == "k_fw2":                      # k_fw2<MODE, COARSE, ...>: BA, X1, X2, X3
+        return FWD[a]
+    if k == "k_proj_tc":                  # MODE 0: activations (forward / dgrad share the kernel), MODE 1: weight gradient
+        return "proj_wgrad" if a == 1 else "proj_act"
+    if k == "k_proj_wprep":
+        return "proj_act"
     if k == "k_block_stage":
         return FWD[a]
     if k == "k_block_bwd_stage":
