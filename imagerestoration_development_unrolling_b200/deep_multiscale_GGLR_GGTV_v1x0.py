@@ -237,6 +237,44 @@ def set_host_cnn_kernels(on: bool) -> bool:
     return prev
 
 
+FILTER_STREAMS = False
+_side_streams = {}
+
+
+def set_filter_streams(on: bool) -> bool:
+    """Opt-in: `AbtractMultiScaleGraphFilter.filtering` runs its four LocalLowpassFilteringBlocks on four CUDA streams (the
+    caller's stream + three side streams, fork / join by events) - the blocks are independent (V1X0:1117-1131).  The same
+    kernels and results; it shortens the latency of small batches, where one block cannot fill 148 SMs (tools/bench_config1.py),
+    and it is capturable in a CUDA graph.  Autograd runs each block's backward on the stream its forward ran on.  Returns the
+    previous setting."""
+    global FILTER_STREAMS
+    prev, FILTER_STREAMS = FILTER_STREAMS, bool(on)
+    return prev
+
+
+def run_blocks_on_streams(blocks, inputs):
+    """outs[i] = blocks[i](inputs[i]); block 0 on the current stream, the others on per-device side streams that fork from and
+    join back into it."""
+    cur = torch.cuda.current_stream(inputs[0].device)
+    key = (inputs[0].device.index, len(blocks) - 1)
+    if key not in _side_streams:
+        _side_streams[key] = [torch.cuda.Stream(inputs[0].device) for _ in range(len(blocks) - 1)]
+    side = _side_streams[key]
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    outs = [None] * len(blocks)
+    for i in range(1, len(blocks)):
+        side[i - 1].wait_event(fork)
+        with torch.cuda.stream(side[i - 1]):
+            outs[i] = blocks[i](inputs[i])
+        inputs[i].record_stream(side[i - 1])              # the caching allocator must not recycle them under the side stream
+    outs[0] = blocks[0](inputs[0])
+    for i in range(1, len(blocks)):
+        cur.wait_stream(side[i - 1])
+        outs[i].record_stream(cur)
+    return outs
+
+
 class LocalNonLinearBlock(nn.Module):
     """V1X0:951-964."""
 
@@ -338,7 +376,10 @@ class AbtractMultiScaleGraphFilter(nn.Module):
         return tuple(outs)
 
     def filtering(self, coefs):
-        return tuple(getattr(self, f"localfilter_scale_0{i}")(c) for i, c in enumerate(coefs))
+        blocks = [getattr(self, f"localfilter_scale_0{i}") for i in range(len(coefs))]
+        if FILTER_STREAMS and coefs[0].is_cuda and not torch.compiler.is_compiling():
+            return tuple(run_blocks_on_streams(blocks, list(coefs)))
+        return tuple(b(c) for b, c in zip(blocks, coefs))
 
     def decode(self, coefs):
         x = coefs[3]

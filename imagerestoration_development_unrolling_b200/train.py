@@ -42,7 +42,15 @@ def _v7(device=None, **kw):
     return M.MultiScaleSequenceDenoiser(device=torch.device(device) if device is not None else torch.device("cuda"), **kw)
 
 
-MODEL_TYPES: Dict[str, Callable[..., nn.Module]] = {"AbtractMultiScaleGraphFilter": _v13, "MultiScaleSequenceDenoiser": _v7}
+def _v1(device=None, **kw):
+    from . import model_GLR_GTV_deep_v1 as M
+    return M.MultiScaleSequenceDenoiser(device=torch.device(device) if device is not None else torch.device("cuda"), **kw)
+
+
+# "MultiScaleSequenceDenoiser" = the v7 model that scripts/run_lightformer_GGTV_GGLR_multiblocks.py trains; "..._v1" = the older
+# three-block chain (exploration/model_multiscale_mixture_GLR/lib/model_GLR_GTV_deep_v1.py)
+MODEL_TYPES: Dict[str, Callable[..., nn.Module]] = {"AbtractMultiScaleGraphFilter": _v13, "MultiScaleSequenceDenoiser": _v7,
+                                                    "MultiScaleSequenceDenoiser_v1": _v1}
 
 V13_ARGS = dict(n_channels_in=3, n_channels_out=3, dims=[48, 96, 192, 384], hidden_dims=[96, 192, 384, 768], nsubnets=[1, 1, 1, 1],
                 ngraphs=[8, 16, 16, 32], num_blocks=[4, 6, 6, 8], num_blocks_out=4)       # scripts_v2:120-129
@@ -56,7 +64,7 @@ def build_model(conf: dict, device=None) -> nn.Module:
         raise KeyError(f"model.type {kind!r}: known types are {sorted(MODEL_TYPES)}")
     args = dict(V13_ARGS) if kind == "AbtractMultiScaleGraphFilter" else {}
     args.update(conf.get("args") or {})
-    if kind == "MultiScaleSequenceDenoiser" and device is not None:
+    if kind.startswith("MultiScaleSequenceDenoiser") and device is not None:
         args.setdefault("device", device)
     return MODEL_TYPES[kind](**args)
 

@@ -190,3 +190,41 @@ def test_oracle_generalised_solver_matches_reference_glr_only(golden_dir):
         ref = g["grad." + k]
         mask = ref != 0
         assert torch.equal(gr != 0, mask) and rel(gr[mask], ref[mask]) < 1e-11, k
+
+
+# ---- the v1 three-block chain
+def test_v1_denoiser_state_dict_layout(golden_dir):
+    """same keys and parameter count as the reference's v1 MultiScaleSequenceDenoiser (recorded by make_golden_v1_denoiser.py)"""
+    from imagerestoration_development_unrolling_b200 import model_GLR_GTV_deep_v1 as M1
+    m = M1.MultiScaleSequenceDenoiser(torch.device("cpu"))
+    z = np.load(os.path.join(golden_dir, "v1_denoiser.npz"))
+    assert sorted(m.state_dict().keys()) == [str(k) for k in z["keys"]]
+    assert sum(p.numel() for p in m.parameters()) == int(z["n_params"]) == 8282532
+    assert [m.mixtureGLR_block01.GTVmodule00.n_edges, m.mixtureGLR_block03.GTVmodule00.n_edges] == [8, 24]
+
+
+@pytest.mark.gpu
+def test_v1_three_block_denoiser_matches_reference(golden_dir):
+    """forward and backward of the whole v1 chain (three MixtureGTV blocks, 8 / 8 / 24 edges, schedule 2 + 4, SharpeningBlocks
+    between) against the reference run in fp64 on the same deterministic parameters (tests/golden/v1_fill.py)"""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from v1_fill import fill_
+    from imagerestoration_development_unrolling_b200 import model_GLR_GTV_deep_v1 as M1
+    z = np.load(os.path.join(golden_dir, "v1_denoiser.npz"))
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        m = fill_(M1.MultiScaleSequenceDenoiser(torch.device("cpu"))).cuda()
+        x = torch.from_numpy(z["x"]).float().cuda().requires_grad_(True)
+        out = m(x)
+        keys = [k[5:] for k in z.files if k.startswith("grad.")]
+        params = dict(m.named_parameters())
+        grads = torch.autograd.grad(out, [x] + [params[k] for k in keys], torch.from_numpy(z["gout"]).float().cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert rel(out, torch.from_numpy(z["out"])) < 1e-4, rel(out, torch.from_numpy(z["out"]))
+    assert rel(grads[0], torch.from_numpy(z["gx"])) < 1e-3, rel(grads[0], torch.from_numpy(z["gx"]))
+    for k, g in zip(keys, grads[1:]):
+        ref = torch.from_numpy(z["grad." + k])
+        assert rel(g, ref) < 2e-3 or float((g.cpu().double() - ref).abs().max()) < 1e-6 * max(1.0, float(ref.abs().max())), (k, rel(g, ref))

@@ -87,6 +87,7 @@ def test_png_crop_psnr_within_0p01_db_of_the_reference(golden_dir):
     assert abs(evalpipe.evaluate(m, [noisy, noisy], [clean, clean]) - psnr) < 1e-4
 
 
+@pytest.mark.gpu
 def test_executor_on_a_cbsd68_sized_image(golden_dir):
     """CBSD68 images are 321 x 481 -> padded to 336 x 496: the 1/8-scale planes are 42 x 62 (W % 4 == 2), outside the host-CNN
     kernels and the streaming filter kernels.  The inference executor must fall back per scale and give the module's result
@@ -106,3 +107,39 @@ def test_executor_on_a_cbsd68_sized_image(golden_dir):
     assert rel(out, ref) < 1e-4, rel(out, ref)
     a, b = evalpipe.restore_image(m, noisy), evalpipe.restore_image(evalpipe.inference_executor(m), noisy)
     assert a.shape == (1, 3, 321, 481) and float((a - b).abs().max()) <= 1.0
+
+
+@pytest.mark.gpu
+def test_four_stream_filtering_equals_the_sequential_blocks(golden_dir):
+    """set_filter_streams(True): the four filter blocks on four streams (V1X0:1117-1131: independent) - the same outputs bit for
+    bit, the same gradients up to the order of the floating-point atomics, also when captured into a CUDA graph"""
+    from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
+    z = _load(golden_dir)
+    m = M.AbtractMultiScaleGraphFilter(**CFG)
+    m.load_state_dict({str(k): torch.from_numpy(z["sd." + str(k)]) for k in z["keys"]}, strict=True)
+    m = m.cuda().train()
+    noisy = torch.from_numpy(z["noisy"]).float().cuda()
+    params = [p for p in m.parameters()]
+
+    def run():
+        out = m(noisy)
+        grads = torch.autograd.grad(out.square().mean(), params)
+        return out.detach(), grads
+
+    out1, g1 = run()
+    prev = M.set_filter_streams(True)
+    try:
+        out2, g2 = run()
+        with torch.no_grad():
+            m(noisy)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out3 = m(noisy)
+            graph.replay()
+            torch.cuda.synchronize()
+    finally:
+        M.set_filter_streams(prev)
+    assert torch.equal(out1, out2) and torch.equal(out3, out1)
+    for a, b in zip(g1, g2):
+        assert rel(b, a) < 1e-4 or float(a.abs().max()) < 1e-12

@@ -46,7 +46,27 @@ with torch.no_grad():
     e1.record()
     torch.cuda.synchronize()
     ms_graph = e0.elapsed_time(e1) / n
+    # the four blocks on four streams (V1X0:1117-1131: they are independent), eager and as one CUDA graph with four branches
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    ms_streams = timed(lambda: M.run_blocks_on_streams(gpu, xg))
+    g4 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g4):
+        outs_4 = M.run_blocks_on_streams(gpu, xg)
+    ms_graph4 = timed(g4.replay)
+    same = all(torch.equal(a, b) for a, b in zip(outs_4, outs_g))
+    per_block = [timed(lambda b=b, x=x: b(x)) for b, x in zip(gpu, xg)]
 pix = B * RES * RES
 print(json.dumps({"config": "config 1: four filter blocks, forward, 4x3x128x128", "gpu_ms": ms_gpu, "gpu_cuda_graph_ms": ms_graph,
+                  "gpu_four_streams_ms": ms_streams, "gpu_four_streams_cuda_graph_ms": ms_graph4, "four_streams_bit_equal": same,
+                  "per_block_eager_ms": per_block,
                   "gpu_Mpix_per_s": pix / ms_gpu / 1e3, "gpu_graph_Mpix_per_s": pix / ms_graph / 1e3,
                   "finite": bool(all(torch.isfinite(o).all() for o in outs_g))}))

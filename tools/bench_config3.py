@@ -32,7 +32,8 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     steps, warmup, B, R = flag("--steps", 10), flag("--warmup", 3), flag("--batch", 4), flag("--res", 64)
     torch.manual_seed(0)
-    model = T.build_model({"type": "MultiScaleSequenceDenoiser"}, dev).to(dev).train()
+    family = "v1" if "--v1" in sys.argv else "v7"                  # --v1: the three-block chain
+    model = T.build_model({"type": "MultiScaleSequenceDenoiser" + ("_v1" if family == "v1" else "")}, dev).to(dev).train()
     opt, sched = T.build_optimizer(model)
     params = [p for p in model.parameters() if p.requires_grad]
     data = T.SyntheticNoisyPatches(patch_size=R, lambda_noise=15.0, max_num_patchs=B * world * 4)
@@ -74,7 +75,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "train_Mpix_per_s", "value": world * B * R * R / ms / 1e3, "unit": "Mpix/s", "n_gpus": world, "steps": steps,
                           "warmup": warmup, "ms_per_step": ms, "scaling": "weak", "dtype": "f32", "data": "synthetic", "loss": float(loss),
-                          "config": {"workload": f"v7 MultiScaleSequenceDenoiser, {B} x 3 x {R} x {R} per GPU, sigma 15, fwd + bwd + all-reduce + Adam",
+                          "config": {"workload": f"{family} MultiScaleSequenceDenoiser, {B} x 3 x {R} x {R} per GPU, sigma 15, fwd + bwd + all-reduce + Adam",
                                      "params": sum(p.numel() for p in params)}}))
     if world > 1:
         dist.destroy_process_group()
