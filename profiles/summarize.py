@@ -5,6 +5,7 @@
 """
 import collections
 import csv
+import re
 import subprocess
 import sys
 
@@ -51,9 +52,10 @@ def launch_table(path, out):
     out.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for n, v in tot.most_common(30):
         out.write(f"| `{n}` | {cnt[n]} | {v / 1e3:.1f} | {100 * v / S:.1f}% |\n")
-    own = sum(v for n, v in tot.items() if "void k_" in n or n.startswith("k_"))
-    out.write(f"\nown kernels (k_*): {100 * own / S:.1f}% of the captured GPU time; the rest are the library GEMMs of the two "
-              "feature projections (cuBLAS fp32 SIMT, TF32 off for parity) and elementwise glue.\n\n")
+    own = sum(v for n, v in tot.items() if re.search(r"(^|::|\s)k_", n))
+    lib = [n for n in tot if "cutlass" in n or "sgemm" in n or "cublas" in n.lower() or "gemm" in n.lower()]
+    out.write(f"\nown kernels (k_*): {100 * own / S:.1f}% of the captured GPU time; library GEMM kernels in the list: "
+              f"{', '.join(lib) if lib else 'none'}; the rest is torch elementwise glue (fills of the gradient accumulators, adds).\n\n")
 
 
 def full_table(rep, out):
@@ -75,15 +77,19 @@ def full_table(rep, out):
 
 
 if __name__ == "__main__":
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    import json, os
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+    # r01: gpurun_out/launches_r01b.csv + prof_r01_stream_raw.csv; r02: r02_launches_all.csv + r02_{bw2,fwd,proj}_raw.csv
+    launches = f"gpurun_out/launches_{tag}b.csv" if tag == "r01" else f"gpurun_out/{tag}_launches_all.csv"
+    raws = [f"gpurun_out/prof_{tag}_stream_raw.csv"] if tag == "r01" else [f"gpurun_out/{tag}_{k}_raw.csv" for k in ("bw2", "fwd", "proj")]
     with open(f"profiles/{tag}_summary.md", "w") as out:
         out.write(f"# ncu summary, round {tag}\n\n"
-                  "Launch list and per-slot DRAM traffic: one step of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (the\n"
-                  "benchmark sizes, batch 32).  Full capture: `python tools/fwd_stage_times.py --scales 0 --reps 1 --bwd` - the 17\n"
-                  "streaming kernels of one forward + backward of the scale-0 block [32,48,256,256].\n"
-                  "Numbers under ncu are never bench values (cold cache, serialised); they explain where the time goes.\n\n")
-        launch_table(f"gpurun_out/launches_{tag}b.csv", out)
-        import json, os
+                  "Launch list: the whole process `python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-infer4k`\n"
+                  "(benchmark sizes, batch 32: 3 warm-up + 1 timed + 3 end-to-end steps).  Per-slot DRAM traffic: the timed step of the same\n"
+                  "command.  Full captures (`ncu --set full --clock-control none --import-source on`): the scale-0 launches of the same\n"
+                  "command (`tools/gpu_round2_profile.sh`).  Numbers under ncu are never bench values (cold cache, serialised); they\n"
+                  "explain where the time goes.\n\n")
+        launch_table(launches, out)
         sp = f"profiles/{tag}_step_slots.json"
         if os.path.exists(sp):
             d = json.load(open(sp))["slots"]
@@ -92,5 +98,7 @@ if __name__ == "__main__":
             for k, v in sorted(d.items(), key=lambda kv: -kv[1]["ncu_ms"]):
                 out.write(f"| {k} | {v['launches']} | {v['ncu_ms']:.3f} | {100 * v['share_of_own_kernels']:.1f}% | {v['dram_bytes'] / 1e9:.3f} |\n")
             out.write("\n")
-        full_table(f"gpurun_out/prof_{tag}_stream_raw.csv", out)
+        for r in raws:
+            if os.path.exists(r):
+                full_table(r, out)
     print("wrote", f"profiles/{tag}_summary.md")

@@ -36,6 +36,9 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
+    if "--fw2" in sys.argv:               # forward stages on the pair walkers (csrc/fw2.cuh)
+        from imagerestoration_development_unrolling_b200 import _lib as L
+        L.load().glrgtv_set_fwd_kernels(2)
     blocks = [M.LocalLowpassFilteringBlock(d, 1, g).to(dev) for d, g in zip(DIMS, NG)]
     strips = []
     for s, d in enumerate(DIMS if "--model" not in sys.argv else []):
@@ -87,7 +90,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "infer_Mpix_per_s", "value": H0 * W0 / ms / 1e3, "unit": "Mpix/s", "n_gpus": world,
                           "ms_per_image": ms, "scaling": "strong", "dtype": "f32", "data": "synthetic",
-                          "steps": steps, "warmup": warmup,
+                          "steps": steps, "warmup": warmup, "fw2": "--fw2" in sys.argv,
                           "config": {"workload": ("whole v13 network, one 3840x2160 image, row strips, one row per 3x3 convolution + 8-row halo "
                                                   "exchange per solver stage, LocalNonLinearBlocks on "
                                                   + ("the PyTorch modules" if "--torch-cnn" in sys.argv else "libglrgtv kernels + cuBLAS")) if whole else

@@ -14,12 +14,14 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--path", type=int, default=0)
 ap.add_argument("--scales", default="0,1,2,3")
 ap.add_argument("--tma", type=int, default=0, help="0 auto, 1 cp.async, 2 TMA")
+ap.add_argument("--fw2", action="store_true", help="forward stages on the pair walkers (csrc/fw2.cuh)")
 a = ap.parse_args()
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 lib = L.load()
 lib.glrgtv_set_block_path(a.path)
 lib.glrgtv_set_stream_loader(a.tma)
+lib.glrgtv_set_fwd_kernels(2 if a.fw2 else 1)
 SLOTS = ["fwd_weights", "fwd_BA", "fwd_X1", "fwd_X2", "fwd_X3", "bwd_X3", "bwd_X2", "bwd_X1", "bwd_BA", "bwd_weights"]
 dev = torch.device("cuda")
 out = {}
@@ -46,4 +48,4 @@ for s, (d, g) in enumerate(zip([48, 96, 192, 384], [8, 16, 16, 32])):
     ms = (ctypes.c_float * 16)(); n = (ctypes.c_int * 16)()
     lib.glrgtv_profile_read(ms, n, 16)
     out[f"scale{s}"] = {SLOTS[i]: round(ms[i] / a.reps, 3) for i in range(len(SLOTS)) if n[i]}
-print(json.dumps({"lib": os.environ.get("GLRGTV_LIB", "default"), "batch": a.batch, "res": a.res, "path": a.path, "tma": a.tma, **out}))
+print(json.dumps({"lib": os.environ.get("GLRGTV_LIB", "default"), "batch": a.batch, "res": a.res, "path": a.path, "tma": a.tma, "fw2": a.fw2, **out}))

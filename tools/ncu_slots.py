@@ -20,7 +20,7 @@ PLANE_BWD = ["bwd_X3", "bwd_X2", "bwd_X1", "bwd_BA"]
 
 
 def slot_of(name):
-    m = re.match(r"(?:void )?(k_\w+)(?:<(?:\(int\))?(\d+))?", name)
+    m = re.search(r"\b(k_\w+)(?:<(?:\(int\))?(\d+))?", name)      # also "void <unnamed>::k_proj_tc<0>(...)"
     if not m:
         return None
     k, a = m.group(1), int(m.group(2)) if m.group(2) else 0
