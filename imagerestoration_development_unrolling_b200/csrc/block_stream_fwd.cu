@@ -714,7 +714,7 @@ static int launch_stream_kernel(const StreamFwdArgs& a, const StreamPlan& p, lon
     return GLRGTV_OK;
 }
 // second-generation pair walkers (fw2.cuh; instantiated in fw2_<stage>.cu)
-extern int g_glr_fw2;
+bool glr_fw2_wanted(int mode, const glrgtv_shape* s);
 bool glr_fw2_eligible(const glrgtv_shape* s);
 extern template int glr_fw2_stage<FW_BA>(F2Args, const float*, const float*, const float*, float*, int, int, void*);
 extern template int glr_fw2_stage<FW_X1>(F2Args, const float*, const float*, const float*, float*, int, int, void*);
@@ -737,7 +737,7 @@ static int glr_fw2_dispatch(int mode, const StreamFwdArgs& a, void* stream) {
 template <int MODE>
 static int launch_stream_stage(StreamFwdArgs a, void* stream) {
     const glrgtv_shape& s = a.s;
-    if (g_glr_fw2 && a.vc != nullptr && glr_fw2_eligible(&s)) {
+    if (a.vc != nullptr && glr_fw2_wanted(MODE, &s) && glr_fw2_eligible(&s)) {
         GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_BA + MODE, stream);
         const int rc2 = glr_fw2_dispatch(MODE, a, stream);
         GLR_PROF_END(GLRGTV_SLOT_FWD_BA + MODE, stream);

@@ -219,9 +219,10 @@ int glrgtv_set_stream_loader(int mode);
  * into the adjoint walk; W % 4 == 0, all channels of a graph in one CTA), 1 = the round-1 walkers + separate gradient pass.
  * Same results; a test / comparison switch. */
 int glrgtv_set_bwd_kernels(int generation);
-/* Forward stage kernels: 1 (default) = the round-1 walkers of csrc/block_stream_fwd.cu, 2 = the pair walkers of
- * csrc/fw2.cuh (W % 8 == 0, any width in column strips; need the scratch glrgtv_block_saved.vc).  Same results; the
- * pair walkers measured no faster on a B200 (profiles/r02_summary.md) and stay a tested opt-in. */
+/* Forward stage kernels: 0 (default) = automatic per stage and plane width, 1 = always the round-1 quad walkers of
+ * csrc/block_stream_fwd.cu, 2 = the pair walkers of csrc/fw2.cuh wherever the shape allows (W % 8 == 0, any width in column
+ * strips; they need the scratch glrgtv_block_saved.vc).  Same results; the automatic rule follows the B200 measurements in
+ * profiles/r02_configs.md (pair walkers on planes of <= 64 columns and for the BA / X2 stages at 128 columns). */
 int glrgtv_set_fwd_kernels(int generation);
 /* streaming-path kernels launched since the library was loaded (diagnostic: lets a test assert which path ran) */
 unsigned long long glrgtv_stream_launch_count(void);

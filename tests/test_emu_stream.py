@@ -64,7 +64,7 @@ def test_stream_block_forward(case, generation):
     n0 = E.emu_lib().glrgtv_stream_launch_count()
     E.call("glrgtv_block_fwd", L.make_shape(B, G, F, H, W), p, x, f0, f1, out, sv, None)
     nl = E.emu_lib().glrgtv_stream_launch_count() - n0
-    E.emu_lib().glrgtv_set_fwd_kernels(1)
+    E.emu_lib().glrgtv_set_fwd_kernels(0)
     # round 1: one launch per stage; fw2: a half-resolution and a full-resolution launch per stage
     assert nl == (8 if generation == 2 and fw2_eligible(F, H, W) else 4), nl
     for n in ("wT0", "wL0", "wT1", "wL1"):

@@ -21,11 +21,12 @@ def M():
 def lib():
     from imagerestoration_development_unrolling_b200 import _lib as L
     lib = L.load()
-    yield lib
+    lib.glrgtv_set_fwd_kernels(1)            # the launch counts asserted below are those of one forward generation; the automatic
+    yield lib                                # per-stage choice (the library default) has its own test at the end of the file
     lib.glrgtv_set_block_path(0)
     lib.glrgtv_set_stream_loader(0)
     lib.glrgtv_set_bwd_kernels(2)
-    lib.glrgtv_set_fwd_kernels(1)
+    lib.glrgtv_set_fwd_kernels(0)
 
 
 # every walker width (8 / 16 / 32 / 64 lanes), partial walkers, F = 6 and 12, several channels per CTA
@@ -279,3 +280,22 @@ def test_forward_pair_walkers_on_a_4k_wide_plane(M, lib):
         out2 = blk(x)
         assert lib.glrgtv_stream_launch_count() - n0 == 8
     assert rel(out2, out1) < 2e-6, rel(out2, out1)
+
+
+@pytest.mark.parametrize("scale", [0, 1, 2, 3])
+def test_automatic_forward_choice(M, lib, scale):
+    """glrgtv_set_fwd_kernels(0), the library default: pair walkers on planes of <= 64 columns and for BA / X2 at 128 columns,
+    quad walkers elsewhere (profiles/r02_configs.md) - same results as either generation alone"""
+    dim, G = [48, 96, 192, 384][scale], [8, 16, 16, 32][scale]
+    B, H = 2, 256 >> scale
+    sd = random_block_state(dim, G, seed=41 + scale)
+    x = torch.randn(B, dim, H, H, generator=torch.Generator().manual_seed(50 + scale)).cuda()
+    blk = make_block(M, dim, G, sd)
+    with torch.no_grad():
+        lib.glrgtv_set_fwd_kernels(1)
+        out1 = blk(x)
+        lib.glrgtv_set_fwd_kernels(0)
+        n0 = lib.glrgtv_stream_launch_count()
+        out0 = blk(x)
+        assert lib.glrgtv_stream_launch_count() - n0 == [4, 6, 8, 8][scale]
+    assert rel(out0, out1) < 2e-6, rel(out0, out1)
