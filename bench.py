@@ -231,7 +231,9 @@ def infer4k(blocks, dev, rank, world, steps=3, warmup=2):
     strips = []
     for s, d in enumerate(DIMS):
         a, b = shard.strip_bounds(H0 >> s, world, align=2)[rank]
-        strips.append(torch.randn(1, d, b - a, W0 >> s, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + s)))
+        x = shard.strip_with_halo_room((1, d, b - a, W0 >> s), rank, world, device=dev)     # the rank's strip, with room for the halo rows
+        x.copy_(torch.randn(1, d, b - a, W0 >> s, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + s)))
+        strips.append(x)
 
     def run():
         with torch.no_grad():
@@ -285,7 +287,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL's stream at high priority: a halo exchange started while the interior rows of a stage are still being computed gets
+        # SMs as CTAs retire instead of waiting behind the whole stage kernel (profiles/r02_scaling.md)
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     torch.backends.cudnn.allow_tf32 = False           # fp32 projections: the parity setting is the measured one
     torch.backends.cuda.matmul.allow_tf32 = False
     lib = L.load()

@@ -1,5 +1,5 @@
 """Inference forward of the host CNN's LocalNonLinearBlock (V1X0:911-964) on the library's kernels (SURVEY 8f rank 1,
-first cut: the HBM-bound part; the two 1x1 convolutions stay cuBLAS fp32 GEMMs).
+the HBM-bound pieces on own kernels; the two 1x1 convolutions on the tcgen05 three-pass-TF32 GEMM of csrc/proj_tc.cu, see GEMM).
 
     reference                                   here
     n = w_n * x / sqrt(var_c(x) + 1e-5)         rs = glrgtv_pixel_rstd(x)                       (x read once)
@@ -15,6 +15,19 @@ from typing import Callable, Optional, Tuple
 import torch
 
 NORM_EPS = 1e-5      # V1X0:921
+# the two 1x1 convolutions of the inference forward: "tc" = libglrgtv's tcgen05 three-pass-TF32 GEMM (csrc/proj_tc.cu, the
+# projection kernel of the filter blocks; fp32-level accuracy), "cublas" = torch.matmul (fp32 SIMT with TF32 off); "auto" = "tc"
+# on CUDA tensors whose extents the kernel takes (multiples of 4, one sub-network), else the library GEMM
+GEMM = "auto"
+
+
+def _mm(w: torch.Tensor, x3: torch.Tensor) -> torch.Tensor:
+    """w [nsub, M, K], x3 [B, nsub, K, N] -> [B, nsub, M, N]"""
+    if GEMM != "cublas" and x3.is_cuda and w.shape[0] == 1:
+        from . import ops
+        if ops.proj_supported(w.shape[1], w.shape[2], x3.shape[-1]):
+            return ops.proj_gemm(w[0], x3[:, 0], False).unsqueeze(1)
+    return torch.matmul(w, x3)
 
 
 class CudaCnnKernels:
@@ -60,14 +73,14 @@ def nonlinear_block_forward(blk, x: torch.Tensor, kernels=None,
     w1, w9, w2, s0 = folded_weights(blk)
     x = x.contiguous()
     rs = kernels.pixel_rstd(x, nsub, NORM_EPS)                                          # [B, nsub, H, W]
-    h = torch.matmul(w1, x.view(B, nsub, C // nsub, H * W)).view(B, -1, H, W)           # [B, 2Hd, H, W], un-normalised
+    h = _mm(w1, x.view(B, nsub, C // nsub, H * W)).view(B, -1, H, W)                    # [B, 2Hd, H, W], un-normalised
     top = bot = None
     if exchange is not None:
         per = h.shape[1] // nsub
         scaled = lambda r: (h[:, :, r].view(B, nsub, per, W) * rs[:, :, r].unsqueeze(2)).reshape(B, -1, W).contiguous()  # noqa: E731
         top, bot = exchange(scaled(0), scaled(H - 1))
     u = kernels.dwconv_gate(h, rs, w9, top, bot)                                        # [B, Hd, H, W]
-    y = torch.matmul(w2, u.view(B, nsub, -1, H * W)).view(B, C, H, W)
+    y = _mm(w2, u.view(B, nsub, -1, H * W)).view(B, C, H, W)
     return torch.addcmul(y, x, s0)
 
 

@@ -689,6 +689,39 @@ def lowpass_block_stage(stage: int, x: Tensor, feat0, feat1, params: Sequence[Te
           feat0, feat1, out, sv, int(row0), int(row1))
 
 
+class PreparedBlockStages:
+    """glrgtv_block_fwd_stage with everything marshalled ONCE per plane: the shape, parameter and saved-tensor structs are built (and
+    the tensors type-checked) here, a stage call is then a single ctypes call.  A spatially sharded rank makes five stage calls per
+    block and image on strips that take well under a millisecond each, so rebuilding ~40 struct fields per call was host time on
+    the critical path (tools/strip_host_overhead.py).  Keeps its tensors alive."""
+
+    def __init__(self, x: Tensor, params: Sequence[Tensor], n_graphs: int, saved: Sequence[Tensor], out: Tensor):
+        _chk(x, out, *params, *saved)
+        B, G, F, H, W = _block_geometry(x, n_graphs)
+        self.x, self.out = x, out
+        self.params = [_c(p) for p in params]
+        self.saved = list(saved)
+        self._shape = L.make_shape(B, G, F, H, W)
+        self._p = _block_structs(self.params)
+        self._sv = L.BlockSaved(*[t.data_ptr() for t in saved])
+        self._fn = getattr(_lib(), "glrgtv_block_fwd_stage")
+        import ctypes as C
+        self._args = (C.byref(self._shape), C.byref(self._p), x.data_ptr())
+        self._tail = (out.data_ptr(), C.byref(self._sv))
+
+    def run(self, stage: int, feat0, feat1, row0: int, row1: int) -> None:
+        global launch_count
+        launch_count += 1
+        x = self.x
+        with torch.cuda.device(x.device):
+            if x.device.index not in _checked_devices:
+                L.check(_lib().glrgtv_check_device(), _lib(), f"check_device({x.device})")
+                _checked_devices.add(x.device.index)
+            rc = self._fn(int(stage), *self._args, None if feat0 is None else feat0.data_ptr(), None if feat1 is None else feat1.data_ptr(),
+                          *self._tail, int(row0), int(row1), _stream(x))
+        L.check(rc, _lib(), "glrgtv_block_fwd_stage")
+
+
 def alloc_block_saved(x: Tensor, n_graphs: int) -> List[Tensor]:
     B, G, F, H, W = _block_geometry(x, n_graphs)
     return [x.new_empty(s) for s in _saved_shapes(B, G, F, H, W)]

@@ -10,6 +10,7 @@ the B200-side addition, one process per GPU over torch.distributed (NCCL on GPUs
   aligned) makes the strip result exact: rows contaminated by the artificial strip border are cropped away, true
   image borders keep the reference's padding rules because no halo is added there.
 """
+import contextlib
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
@@ -149,13 +150,14 @@ class CudaStageRunner:
         feat0, feat1 = lf._projections(ext)                   # per-pixel / 2x2-aligned: valid on the halo rows too
         params = lf._block_params() + [self.blk.skip_weight]
         saved = ops.alloc_block_saved(ext, lf.n_graphs)
-        st = dict(ext=ext, params=params, saved=saved, names=dict(zip(ops._SAVED, saved)), out=torch.empty_like(ext))
-        ops.lowpass_block_stage(0, ext, feat0.contiguous(), feat1.contiguous(), params, lf.n_graphs, saved, st["out"], 0, ext.shape[-2])
+        out = torch.empty_like(ext)
+        calls = ops.PreparedBlockStages(ext, params, lf.n_graphs, saved, out)      # structs marshalled once per plane
+        st = dict(ext=ext, calls=calls, names=dict(zip(ops._SAVED, saved)), out=out)
+        calls.run(0, feat0.contiguous(), feat1.contiguous(), 0, ext.shape[-2])
         return st
 
     def stage(self, st, k: int, row0: int, row1: int) -> None:
-        from . import ops
-        ops.lowpass_block_stage(k, st["ext"], None, None, st["params"], self.lf.n_graphs, st["saved"], st["out"], row0, row1)
+        st["calls"].run(k, None, None, row0, row1)
 
     def buffer(self, st, name: str) -> torch.Tensor:
         return st["names"][name].view(st["ext"].shape)        # [B,G,F,H,W] -> [B,C,H,W]
@@ -186,10 +188,11 @@ def sharded_block_forward_staged(blk, strip: torch.Tensor, rank: int, world: int
     return runner.output(st)[..., r0:r1, :].contiguous()
 
 
-def _exchange_many(sends_up: List[Optional[torch.Tensor]], sends_down: List[Optional[torch.Tensor]], rank: int, world: int, group=None):
-    """One batched neighbour exchange for several tensors at once (one NCCL group = one latency instead of one per tensor):
+def _exchange_many_start(sends_up: List[Optional[torch.Tensor]], sends_down: List[Optional[torch.Tensor]], rank: int, world: int, group=None):
+    """Start one batched neighbour exchange for several tensors at once (one NCCL group = one latency instead of one per tensor):
     sends_up[i] goes to rank-1 and is answered by that rank's sends_down[i], and vice versa.  Every rank must pass lists of the
-    same length and order.  Returns (from_up, from_down); entries are None at the true image border."""
+    same length and order.  Returns a handle for `_exchange_many_finish`; work enqueued in between overlaps the transfer (the
+    NCCL stream waits only for what was enqueued BEFORE this call)."""
     ops, from_up, from_down = [], [None] * len(sends_up), [None] * len(sends_down)
     for i, (su, sd) in enumerate(zip(sends_up, sends_down)):
         if rank > 0:
@@ -198,22 +201,96 @@ def _exchange_many(sends_up: List[Optional[torch.Tensor]], sends_down: List[Opti
         if rank < world - 1:
             from_down[i] = torch.empty_like(sd)
             ops += [dist.P2POp(dist.isend, sd, rank + 1, group), dist.P2POp(dist.irecv, from_down[i], rank + 1, group)]
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    return reqs, from_up, from_down, (sends_up, sends_down)       # (the send buffers stay referenced until the exchange is over)
+
+
+def _exchange_many_finish(handle):
+    reqs, from_up, from_down, _ = handle
+    for req in reqs:
+        req.wait()
     return from_up, from_down
+
+
+def _exchange_many(sends_up, sends_down, rank: int, world: int, group=None):
+    return _exchange_many_finish(_exchange_many_start(sends_up, sends_down, rank, world, group))
+
+
+def strip_with_halo_room(shape: Sequence[int], rank: int, world: int, halo: int = STAGE_HALO_ROWS, **kw) -> torch.Tensor:
+    """An uninitialised [B,C,rows,W] row strip allocated INSIDE a buffer that has room for the neighbours' halo rows above and
+    below it (none at the true image border).  A producer that writes its strip into this tensor (an `out=` argument, `copy_`)
+    saves `sharded_filtering_staged` the copy of the whole strip into an extended plane - 1 ms per 4K image and rank on two GPUs
+    (profiles/r02_scaling.md); any other tensor works too and is copied."""
+    B, C, rows, W = shape
+    t, b = (halo if rank > 0 else 0), (halo if rank < world - 1 else 0)
+    ext = torch.empty(B, C, t + rows + b, W, **kw)
+    ext._glrgtv_halo_room = (t, b)                                  # only buffers made here are ever written outside the strip
+    return ext[:, :, t:t + rows, :]
+
+
+def _extended_plane(x: torch.Tensor, t: int, b: int) -> Optional[torch.Tensor]:
+    """the buffer around a strip made by strip_with_halo_room (same halo geometry), else None"""
+    base = getattr(x, "_base", None)
+    if base is None or getattr(base, "_glrgtv_halo_room", None) != (t, b) or base.dim() != 4 or not base.is_contiguous():
+        return None
+    B, C, rows, W = x.shape
+    if tuple(base.shape) != (B, C, t + rows + b, W) or x.storage_offset() != base.storage_offset() + t * W or x.stride() != base.stride():
+        return None
+    return base
+
+
+class _ScaleStreams:
+    """one side stream per scale, forked from / joined to the caller's stream (cached per device)"""
+    _cache = {}
+
+    def __init__(self, ref: torch.Tensor, n: int):
+        key = (ref.device, n)
+        if key not in self._cache:
+            self._cache[key] = [torch.cuda.Stream(device=ref.device) for _ in range(n)]
+        self.side, self.dev = self._cache[key], ref.device
+
+    def fork(self):
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.side:
+            s.wait_stream(cur)
+
+    def on(self, i: int):
+        return torch.cuda.stream(self.side[i])
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.side:
+            cur.wait_stream(s)
+
+
+OVERLAP_MIN_ROWS = 64    # strips at least this tall compute their boundary rows first and overlap the halo exchange with the interior
 
 
 @torch.no_grad()
 def sharded_filtering_staged(blocks: Sequence, strips: Sequence[torch.Tensor], rank: int, world: int, group=None,
-                             runners: Optional[Sequence] = None) -> List[torch.Tensor]:
+                             runners: Optional[Sequence] = None, overlap: bool = True, streams: Optional[bool] = None) -> List[torch.Tensor]:
     """`sharded_block_forward_staged` for several independent filter blocks at once (the four scales of
     AbtractMultiScaleGraphFilter.filtering, V1X0:1117-1131): the blocks advance through the solver stages in lock-step and
     each round's halo rows of ALL blocks travel in ONE batched exchange - 5 exchange rounds per image instead of 5 per block.
-    Same arithmetic, same results as the per-block form."""
+    `overlap`: a stage first produces the 8 rows next to each neighbour (the stage kernels take any even row range), the
+    exchange of those rows starts, and the interior rows are computed while it is in flight; strips shorter than OVERLAP_MIN_ROWS
+    are computed in one piece (two extra launches with a 7-row pipeline fill each would cost more than the exchange hides).
+    Same arithmetic, same results as the per-block form either way.  Returns row VIEWS of the extended output planes; strips made
+    by `strip_with_halo_room` are used in place, others are copied into an extended plane first."""
     n = len(strips)
-    if world == 1 and runners is None:
-        return [blk(x) for blk, x in zip(blocks, strips)]
+    if streams is None:
+        streams = strips[0].is_cuda and n > 1
+    if world == 1 and runners is None:                             # one rank, whole maps: the blocks as they are, one stream per scale
+        if not streams:
+            return [blk(x) for blk, x in zip(blocks, strips)]
+        lanes = _ScaleStreams(strips[0], n)
+        lanes.fork()
+        outs = []
+        for i, (blk, x) in enumerate(zip(blocks, strips)):
+            with lanes.on(i):
+                outs.append(blk(x))
+        lanes.join()
+        return outs
     hr = STAGE_HALO_ROWS
     for x in strips:
         if x.shape[-2] < 2 * hr:
@@ -221,27 +298,67 @@ def sharded_filtering_staged(blocks: Sequence, strips: Sequence[torch.Tensor], r
     runners = list(runners) if runners is not None else [CudaStageRunner(blk) for blk in blocks]
     t, b = (hr if rank > 0 else 0), (hr if rank < world - 1 else 0)
     tops, bots = _exchange_many([x[..., :hr, :].contiguous() for x in strips], [x[..., -hr:, :].contiguous() for x in strips], rank, world, group)
-    states = []
+    # the blocks are independent (V1X0:1117-1131): each scale's kernels go to its own CUDA stream, so the launch-latency-bound
+    # deep scales (a 1/8 strip of the 1/8-resolution map is 34 rows) run beside the large ones instead of after them; every
+    # round joins the streams before the exchange
+    lanes = _ScaleStreams(strips[0], n) if streams else None
+    states = [None] * n
     for i, x in enumerate(strips):
-        parts = ([tops[i]] if tops[i] is not None else []) + [x] + ([bots[i]] if bots[i] is not None else [])
-        states.append(runners[i].prepare(torch.cat(parts, dim=-2).contiguous()))
+        ext = _extended_plane(x, t, b)                             # a strip that already sits inside its extended plane: no copy
+        if ext is None:
+            ext = x.new_empty(x.shape[:-2] + (t + x.shape[-2] + b, x.shape[-1]))
+            ext[..., t:t + x.shape[-2], :] = x
+        if t:
+            ext[..., :t, :] = tops[i]
+        if b:
+            ext[..., t + x.shape[-2]:, :] = bots[i]
+        states[i] = ext
+    if lanes:
+        lanes.fork()
+    for i in range(n):
+        with (lanes.on(i) if lanes else contextlib.nullcontext()):
+            states[i] = runners[i].prepare(states[i])
     ends = [x.shape[-2] + t for x in strips]                       # [t, ends[i]) = this rank's own rows inside the extended plane
+    split = [overlap and world > 1 and x.shape[-2] >= OVERLAP_MIN_ROWS for x in strips]
     for k, produced in ((1, "bA"), (2, "x1"), (3, "x2")):
-        bufs = []
-        for i in range(n):
-            runners[i].stage(states[i], k, t, ends[i])
-            bufs.append(runners[i].buffer(states[i], produced))
-        ups, downs = _exchange_many([bf[..., t:t + hr, :].contiguous() for bf in bufs],
-                                    [bf[..., e - hr:e, :].contiguous() for bf, e in zip(bufs, ends)], rank, world, group)
+        bufs = [runners[i].buffer(states[i], produced) for i in range(n)]
+        for i in range(n):                                         # the rows a neighbour waits for (everything, for short strips)
+            with (lanes.on(i) if lanes else contextlib.nullcontext()):
+                if not split[i]:
+                    runners[i].stage(states[i], k, t, ends[i])
+                else:
+                    if t:
+                        runners[i].stage(states[i], k, t, t + hr)
+                    if b:
+                        runners[i].stage(states[i], k, ends[i] - hr, ends[i])
+        if lanes:
+            lanes.join()
+        handle = _exchange_many_start([bf[..., t:t + hr, :].contiguous() for bf in bufs],
+                                      [bf[..., e - hr:e, :].contiguous() for bf, e in zip(bufs, ends)], rank, world, group)
+        if lanes:
+            lanes.fork()
+        for i in range(n):                                         # interior rows, while the halo rows travel
+            if split[i]:
+                with (lanes.on(i) if lanes else contextlib.nullcontext()):
+                    runners[i].stage(states[i], k, t + (hr if t else 0), ends[i] - (hr if b else 0))
+        if lanes:
+            lanes.join()
+        ups, downs = _exchange_many_finish(handle)
         for bf, e, u, d in zip(bufs, ends, ups, downs):
             if u is not None:
                 bf[..., :t, :] = u
             if d is not None:
                 bf[..., e:, :] = d
+        if lanes:
+            lanes.fork()
     outs = []
     for i in range(n):
-        runners[i].stage(states[i], 4, t, ends[i])
-        outs.append(runners[i].output(states[i])[..., t:ends[i], :].contiguous())
+        with (lanes.on(i) if lanes else contextlib.nullcontext()):
+            runners[i].stage(states[i], 4, t, ends[i])
+    if lanes:
+        lanes.join()
+    for i in range(n):                                             # row views of the extended outputs (no copy; .contiguous() them if needed)
+        outs.append(runners[i].output(states[i])[..., t:ends[i], :])
     return outs
 
 

@@ -198,6 +198,47 @@ def test_staged_sharded_block_equals_full_image(world):
     assert float((got.double() - full).norm() / full.norm()) < 1e-5
 
 
+def _lockstep_worker(rank, world, port, q, sds, xs, G, in_place):
+    _init(rank, world, port)
+    shard.OVERLAP_MIN_ROWS = 24            # strips of 32+ rows: boundary rows first, exchange, interior rows (the overlapped schedule)
+    strips = []
+    for x in xs:
+        a, b = shard.strip_bounds(x.shape[-2], world, align=2)[rank]
+        if in_place:                       # the strip already sits inside a buffer with room for the halo rows: used without a copy
+            s = shard.strip_with_halo_room((x.shape[0], x.shape[1], b - a, x.shape[-1]), rank, world)
+            s._base.fill_(float("nan"))
+            s.copy_(x[:, :, a:b])
+        else:
+            s = x[:, :, a:b].contiguous()
+        strips.append(s)
+    outs = shard.sharded_filtering_staged([None] * len(xs), strips, rank, world, runners=[EmuStageRunner(sd, G) for sd in sds])
+    q.put((rank, [o.contiguous().numpy() for o in outs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,in_place", [(2, True), (3, True), (3, False)])
+def test_lockstep_filtering_with_overlapped_exchange(world, in_place):
+    """shard.sharded_filtering_staged on two maps of different height: boundary rows first, halo exchange in flight during the
+    interior rows (tall strips) or after the whole stage (short strips), strips used in place inside their extended planes -
+    against the whole-image oracle; NaN-filled buffers prove no stage read a row nobody produced or exchanged"""
+    dim, G = 12, 2
+    sds = [random_block_state(dim, G, seed=17), random_block_state(dim, G, seed=18)]
+    xs = [torch.randn(1, dim, 96, 16, generator=torch.Generator().manual_seed(3)), torch.randn(1, dim, 48, 16, generator=torch.Generator().manual_seed(4))]
+    full = [O.lowpass_block_forward({k: v.double() for k, v in sd.items()}, x.double()) for sd, x in zip(sds, xs)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lockstep_worker, args=(r, world, port, q, sds, xs, G, in_place)) for r in range(world)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=300) for _ in range(world))
+    [p.join(60) for p in procs]
+    for i, ref in enumerate(full):
+        got = torch.cat([torch.from_numpy(res[r][i]) for r in range(world)], dim=2)
+        assert got.shape == ref.shape and torch.isfinite(got).all()
+        assert float((got.double() - ref).norm() / ref.norm()) < 1e-5
+
+
 # ----------------------------------------------------------------------------------------------- whole model on strips
 def _tiny_model(seed=3):
     from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M

@@ -32,7 +32,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream="--low-priority-nccl" not in sys.argv)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
@@ -44,7 +45,9 @@ def main():
     for s, d in enumerate(DIMS if "--model" not in sys.argv else []):
         H, W = H0 >> s, W0 >> s
         a, b = shard.strip_bounds(H, world, align=2)[rank]
-        strips.append(torch.randn(1, d, b - a, W, device=dev, generator=torch.Generator(device=dev).manual_seed(s)))
+        x = shard.strip_with_halo_room((1, d, b - a, W), rank, world, device=dev) if "--batched" in sys.argv else torch.empty(1, d, b - a, W, device=dev)
+        x.copy_(torch.randn(1, d, b - a, W, device=dev, generator=torch.Generator(device=dev).manual_seed(s)))
+        strips.append(x)
 
     staged = "--staged" in sys.argv       # one 8-row exchange per solver stage instead of one 26-row exchange per block
     whole = "--model" in sys.argv
@@ -66,9 +69,11 @@ def main():
             if whole:
                 return ex(img)
             if "--batched" in sys.argv:     # lock-step stages, one batched exchange per round for the four scales
-                return shard.sharded_filtering_staged(blocks, strips, rank, world)
+                return shard.sharded_filtering_staged(blocks, strips, rank, world, overlap="--no-overlap" not in sys.argv, streams=False if "--no-streams" in sys.argv else None)
             if staged:
                 return [shard.sharded_block_forward_staged(blk, x, rank, world) for blk, x in zip(blocks, strips)]
+            if world == 1 and "--streams" in sys.argv:       # one GPU: the four blocks on four streams
+                return shard.sharded_filtering_staged(blocks, strips, rank, world)
             return [shard.sharded_block_forward(blk, x, rank, world) for blk, x in zip(blocks, strips)]
 
     for _ in range(warmup):
@@ -87,10 +92,25 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
+    if "--trace" in sys.argv:
+        # GPU timeline of two images on this rank (CUPTI through torch.profiler; nsys is not installed): kernel name, start, duration
+        # in microseconds, in launch order - enough to see where a round's time goes (stage kernels, NCCL SendRecv, copies, gaps)
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(f"gpurun_out/infer4k_trace_rank{rank}of{world}.csv", "w") as f:
+            f.write("start_us,dur_us,name\n")
+            t0 = evs[0].time_range.start if evs else 0
+            for e in evs:
+                f.write(f"{e.time_range.start - t0:.1f},{e.time_range.end - e.time_range.start:.1f},{e.name[:80].replace(',', ';')}\n")
     if rank == 0:
         print(json.dumps({"metric": "infer_Mpix_per_s", "value": H0 * W0 / ms / 1e3, "unit": "Mpix/s", "n_gpus": world,
                           "ms_per_image": ms, "scaling": "strong", "dtype": "f32", "data": "synthetic",
-                          "steps": steps, "warmup": warmup, "fw2": "--fw2" in sys.argv,
+                          "steps": steps, "warmup": warmup, "fw2": "--fw2" in sys.argv, "overlap": "--no-overlap" not in sys.argv,
                           "config": {"workload": ("whole v13 network, one 3840x2160 image, row strips, one row per 3x3 convolution + 8-row halo "
                                                   "exchange per solver stage, LocalNonLinearBlocks on "
                                                   + ("the PyTorch modules" if "--torch-cnn" in sys.argv else "libglrgtv kernels + cuBLAS")) if whole else

@@ -40,13 +40,19 @@ def main():
     with torch.no_grad():
         res = {"shape": [1, dim, H, W], "hidden": hid, "tf32": tf32}
         res["module_ms"] = timed(lambda: blk(x))
+        host_cnn.GEMM = "cublas"
+        res["fused_cublas_ms"] = timed(lambda: host_cnn.nonlinear_block_forward(blk, x))
+        ref_c = host_cnn.nonlinear_block_forward(blk, x)
+        host_cnn.GEMM = "auto"
         res["fused_ms"] = timed(lambda: host_cnn.nonlinear_block_forward(blk, x))
+        res["gemm1_tc_ms"] = timed(lambda: ops.proj_gemm(w1[0], x.view(1, dim, H * W), False))
         rs = ops.pixel_rstd(x, 1, 1e-5)
         h = torch.matmul(w1, x.view(1, 1, dim, H * W)).view(1, -1, H, W)
         u = ops.dwconv_gate(h, rs, w9)
         res["pixel_rstd_ms"] = timed(lambda: ops.pixel_rstd(x, 1, 1e-5))
         res["gemm1_ms"] = timed(lambda: torch.matmul(w1, x.view(1, 1, dim, H * W)))
         res["dwconv_gate_ms"] = timed(lambda: ops.dwconv_gate(h, rs, w9))
+        res["gemm2_tc_ms"] = timed(lambda: ops.proj_gemm(w2[0], u.view(1, hid, H * W), False))
         res["gemm2_skip_ms"] = timed(lambda: torch.addcmul(torch.matmul(w2, u.view(1, 1, hid, H * W)).view_as(x), x, s0))
         px = H * W * 4
         res["pixel_rstd_GBs"] = (dim + 1) * px / res["pixel_rstd_ms"] / 1e6
