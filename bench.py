@@ -441,7 +441,8 @@ def main():
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": int(sum(h.numel() for h in hx[0]) * 4), "d2h_bytes_per_step": 4,
-                    "note": "pinned-host inputs of step i+1 are copied on a side stream while step i computes"},
+                    "note": "pinned-host inputs of step i+1 are copied on a side stream while step i computes; at N > 1 the ranks' copies "
+                            "(755 MB per rank and step: feature maps, not images) share the host's memory channels and PCIe root complexes"},
             "roofline": roofline,
         }
         if i4k is not None:
