@@ -1,15 +1,23 @@
 #!/bin/bash
-# build an experimental variant of the library with extra -D flags: tools/build_variant.sh out.so -DGLR_TH=16 ...
+# Build an experimental variant of the library: the listed sources are recompiled with the extra -D flags, every other object is
+# taken from the regular build (csrc/build/*.o; run `python -m imagerestoration_development_unrolling_b200.build` first).
+#   tools/build_variant.sh variants/ww5.so weights_walk.cu -DWW_FWD_MINB=5
+# Select it with GLRGTV_LIB=variants/ww5.so (tools/*.py, bench.py).
 set -e
 out=$1; shift
+srcs=$1; shift
 cd "$(dirname "$0")/.."
-CUT=$(python -c "from imagerestoration_development_unrolling_b200.build import cutlass_include as c; print(c())")
+C=imagerestoration_development_unrolling_b200/csrc
 objs=""
-for f in imagerestoration_development_unrolling_b200/csrc/*.cu; do
-  o=/tmp/variant_$(basename $f .cu)_$$.o
-  /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O3 --expt-relaxed-constexpr -I$CUT "$@" -c $f -o $o &
-  objs="$objs $o"
+for o in $C/build/*.o; do
+  b=$(basename $o .o)
+  if echo ",$srcs," | grep -q ",$b.cu,"; then
+    v=/tmp/variant_${b}_$$.o
+    /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O3 --expt-relaxed-constexpr "$@" -c $C/$b.cu -o $v
+    objs="$objs $v"
+  else
+    objs="$objs $o"
+  fi
 done
-wait
+mkdir -p "$(dirname $out)"
 /usr/local/cuda/bin/nvcc -shared -o $out $objs -gencode arch=compute_100a,code=sm_100a
-rm -f $objs
