@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-infer4k", action="store_true")
+    ap.add_argument("--streams", action="store_true", help="experiment: the four blocks of a step on four CUDA streams")
     return ap.parse_args()
 
 
@@ -306,8 +307,20 @@ def main():
     gs = [torch.randn(sh, device=dev, generator=gen) for sh in shapes]
     flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
 
+    side = [torch.cuda.Stream(device=dev) for _ in blocks] if a.streams else None
+
     def step(inputs):
-        outs = [blk(x) for blk, x in zip(blocks, inputs)]
+        if side is None:
+            outs = [blk(x) for blk, x in zip(blocks, inputs)]
+        else:                                           # V1X0:1117-1131: the four blocks are independent (autograd runs each block's
+            cur = torch.cuda.current_stream()           # backward on the stream its forward ran on and joins them at the end)
+            outs = []
+            for st, blk, x in zip(side, blocks, inputs):
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    outs.append(blk(x))
+            for st in side:
+                cur.wait_stream(st)
         torch.autograd.backward(outs, gs, inputs=list(inputs) + params)
         if world > 1:                                   # data-parallel training: ONE gradient all-reduce over NVLink
             shard.allreduce_gradients(params, average=False, flat=flat_grad)
@@ -437,7 +450,7 @@ def main():
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_rank_batch": B, "parallelism": f"dp{world}",
-                       "l2": "inputs larger than L2 (755 MB of block inputs per step)", "tf32": False},
+                       "l2": "inputs larger than L2 (755 MB of block inputs per step)", "tf32": False, "streams": 4 if a.streams else 1},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": int(sum(h.numel() for h in hx[0]) * 4), "d2h_bytes_per_step": 4,

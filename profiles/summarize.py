@@ -81,13 +81,13 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     # r01: gpurun_out/launches_r01b.csv + prof_r01_stream_raw.csv; r02: r02_launches_all.csv + r02_{bw2,fwd,proj}_raw.csv
     launches = f"gpurun_out/launches_{tag}b.csv" if tag == "r01" else f"gpurun_out/{tag}_launches_all.csv"
-    raws = [f"gpurun_out/prof_{tag}_stream_raw.csv"] if tag == "r01" else [f"gpurun_out/{tag}_{k}_raw.csv" for k in ("bw2", "fwd", "proj")]
+    raws = [f"gpurun_out/prof_{tag}_stream_raw.csv"] if tag == "r01" else [f"gpurun_out/{tag}_{k}_raw.csv" for k in ("bw2", "fwd", "ww", "proj")]
     with open(f"profiles/{tag}_summary.md", "w") as out:
         out.write(f"# ncu summary, round {tag}\n\n"
                   "Launch list: the whole process `python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-infer4k`\n"
                   "(benchmark sizes, batch 32: 3 warm-up + 1 timed + 3 end-to-end steps).  Per-slot DRAM traffic: the timed step of the same\n"
                   "command.  Full captures (`ncu --set full --clock-control none --import-source on`): the scale-0 launches of the same\n"
-                  "command (`tools/gpu_round2_profile.sh`).  Numbers under ncu are never bench values (cold cache, serialised); they\n"
+                  "command (`tools/gpu_r02_final.sh`).  Numbers under ncu are never bench values (cold cache, serialised); they\n"
                   "explain where the time goes.\n\n")
         launch_table(launches, out)
         sp = f"profiles/{tag}_step_slots.json"

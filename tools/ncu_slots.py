@@ -42,10 +42,12 @@ def slot_of(name):
         return FWD[a]
     if k == "k_block_bwd_stage":
         return PLANE_BWD[a]
-    if k in ("k_block_weights", "k_gtv_coeffs"):
+    if k in ("k_block_weights", "k_gtv_coeffs", "k_weights_walk"):
         return "fwd_weights"
-    if k == "k_block_weights_bwd":
+    if k in ("k_block_weights_bwd", "k_weights_walk_bwd"):
         return "bwd_weights"
+    if k == "k_space_to_depth":
+        return "proj_act"
     return "other:" + k
 
 
