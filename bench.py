@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-infer4k", action="store_true")
-    ap.add_argument("--streams", action="store_true", help="experiment: the four blocks of a step on four CUDA streams")
+    ap.add_argument("--no-streams", action="store_true", help="run the four blocks of a step one after the other on one stream")
     return ap.parse_args()
 
 
@@ -307,10 +307,10 @@ def main():
     gs = [torch.randn(sh, device=dev, generator=gen) for sh in shapes]
     flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
 
-    side = [torch.cuda.Stream(device=dev) for _ in blocks] if a.streams else None
+    side = None if a.no_streams else [torch.cuda.Stream(device=dev) for _ in blocks]
 
-    def step(inputs):
-        if side is None:
+    def step(inputs, serial=False):
+        if side is None or serial:
             outs = [blk(x) for blk, x in zip(blocks, inputs)]
         else:                                           # V1X0:1117-1131: the four blocks are independent (autograd runs each block's
             cur = torch.cuda.current_stream()           # backward on the stream its forward ran on and joins them at the end)
@@ -339,9 +339,10 @@ def main():
         step(xs)
     barrier()
 
-    # ---- timed region (device-resident inputs), per-kernel events on, clocks sampled
+    # ---- timed region (device-resident inputs), clocks sampled.  The four blocks are independent (V1X0:1117-1131) and run on four
+    # streams, so kernels of different blocks overlap here; the per-kernel CUDA-event times behind `roofline` are therefore taken in
+    # a second pass of the same K steps with the blocks one after the other (below), where a kernel has the GPU to itself
     clocks = ClockSampler(local) if rank == 0 else None
-    lib.glrgtv_profile_enable(1)
     launches0 = lib.glrgtv_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -352,7 +353,6 @@ def main():
     e1.record()
     barrier()
     t1 = time.perf_counter()
-    lib.glrgtv_profile_enable(0)
     launches = lib.glrgtv_launch_count() - launches0
     ms = e0.elapsed_time(e1)
     if world > 1:
@@ -360,6 +360,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clk = clocks.stop(t0, t1) if clocks else None
+    # ---- the same K steps serially, per-kernel events on: the roofline pass
+    step(xs, serial=True)
+    barrier()
+    lib.glrgtv_profile_enable(1)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(a.steps):
+        step(xs, serial=True)
+    s1.record()
+    barrier()
+    lib.glrgtv_profile_enable(0)
+    ms_serial = s0.elapsed_time(s1)
     slot_ms = (ctypes.c_float * 16)()
     slot_n = (ctypes.c_int * 16)()
     lib.glrgtv_profile_read(slot_ms, slot_n, 16)
@@ -439,10 +451,13 @@ def main():
             "peak_source": peak_src, "traffic": traffic,
             "note": "a slot = the launches of one solver stage over the four scales (backward stages: a half- and a full-resolution "
                     "launch each, edge-weight gradients included; bwd_X2 = parts A and B); achieved = algorithmic bytes of the "
-                    "slot / its summed CUDA-event time inside the timed region",
+                    "slot / its summed CUDA-event time over K steps run with the four blocks one after the other "
+                    "(serial_ms_per_step), right after the timed region - in the timed region itself the blocks run on four "
+                    "streams and kernels of different blocks overlap",
             "per_kernel": per_kernel,
-            "kernel_share_of_step": round(top_ms_per_step / (ms / a.steps), 4),
-            "own_kernels_share_of_step": round(whole_ms / (ms / a.steps), 4),
+            "serial_ms_per_step": round(ms_serial / a.steps, 4),
+            "kernel_share_of_step": round(top_ms_per_step / (ms_serial / a.steps), 4),
+            "own_kernels_share_of_step": round(whole_ms / (ms_serial / a.steps), 4),
             "whole_block_compulsory_GBs": sum(20 * C * B * (RES >> s) ** 2 for s, C in enumerate(DIMS)) / (ms / a.steps / 1e3) / 1e9,
         }
         line = {
@@ -450,7 +465,7 @@ def main():
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_rank_batch": B, "parallelism": f"dp{world}",
-                       "l2": "inputs larger than L2 (755 MB of block inputs per step)", "tf32": False, "streams": 4 if a.streams else 1},
+                       "l2": "inputs larger than L2 (755 MB of block inputs per step)", "tf32": False, "streams": 1 if a.no_streams else 4},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": int(sum(h.numel() for h in hx[0]) * 4), "d2h_bytes_per_step": 4,

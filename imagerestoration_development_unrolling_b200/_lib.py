@@ -77,6 +77,7 @@ _SIGS = {
     "glrgtv_set_bwd_kernels": (C.c_int, [C.c_int]),
     "glrgtv_set_fwd_kernels": (C.c_int, [C.c_int]),
     "glrgtv_set_weights_kernels": (C.c_int, [C.c_int]),
+    "glrgtv_set_proj_pipeline": (C.c_int, [C.c_int]),
     "glrgtv_weights_walk_launch_count": (C.c_ulonglong, []),
     "glrgtv_profile_read": (C.c_int, [_P(C.c_float), _P(C.c_int), C.c_int]),
     "glrgtv_edge_weights_fwd": (C.c_int, [_P(Shape), _P(Window), fp, fp, fp, fp]),

@@ -413,7 +413,7 @@ def proj_gemm(w: Tensor, x: Tensor, transpose_w: bool) -> Tensor:
     if R != (M if transpose_w else K):
         raise RuntimeError(f"proj_gemm: weight {tuple(w.shape)} does not match input {tuple(x.shape)}")
     y = x.new_empty(B, K if transpose_w else M, N)
-    ws = x.new_empty(2 * M * K)
+    ws = x.new_empty((int(_lib().glrgtv_proj_gemm_workspace_bytes(M, K)) + 3) // 4)      # the weights as pre-split tile images
     _call("glrgtv_proj_gemm", x, int(bool(transpose_w)), B, M, N, K, w, x, y, ws, ws.numel() * 4)
     return y
 

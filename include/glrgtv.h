@@ -257,6 +257,11 @@ int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params* p, const 
                      const float* gout, float* gx, float* gfeat0, float* gfeat1,
                      const glrgtv_block_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Pipeline of the projection GEMM kernels: 0 (default) = tiles are split in place inside their pipeline stage, 1 = raw tiles
+ * land in a deep ring of their own and are split into a shallow ring of operand slots (more HBM bytes in flight per SM;
+ * measured no faster on a B200 - the kernel was bound by its epilogue, profiles/r02_proj_stalls.md - kept as a tested
+ * alternative).  Same arithmetic, same results. */
+int glrgtv_set_proj_pipeline(int which);
 /* ------------------------------------------------------------------------------------------------
  * Feature projections patchs_features_extraction00 / 01 (V1X0:556-612, 712, 725; nn.Conv2d 1x1 and, after a
  * space-to-depth, 2x2 stride 2) on the tcgen05 tensor cores (csrc/proj_tc.cu): kind::tf32 MMAs with TMEM accumulators,
@@ -264,7 +269,8 @@ int glrgtv_block_bwd(const glrgtv_shape* s, const glrgtv_block_params* p, const 
  * All operands row-major, contiguous, 16-byte aligned; M, N (pixels), K % 4 == 0 (tiles are zero-padded by the TMA unit).
  *   transpose_w == 0:  Y[b] (M x N) = W (M x K)   . X[b] (K x N)      forward
  *   transpose_w == 1:  Y[b] (K x N) = W^T (K x M) . X[b] (M x N)      input gradient
- * workspace: glrgtv_proj_gemm_workspace_bytes(M, K) bytes (the weights split into TF32 hi | lo parts).
+ * workspace: glrgtv_proj_gemm_workspace_bytes(M, K) bytes (the weights split into TF32 hi | lo parts and laid out as the
+ * shared-memory tile images the kernel bulk-copies, one per accumulator chunk and 32-wide k-stage).
  * ---------------------------------------------------------------------------------------------- */
 size_t glrgtv_proj_gemm_workspace_bytes(int M, int K);
 int glrgtv_proj_gemm(int transpose_w, int batch, int M, int N, int K, const float* W, const float* X, float* Y,

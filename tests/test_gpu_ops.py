@@ -133,12 +133,22 @@ PROJ_SHAPES = [(2, 96, 48, 64 * 64), (1, 48, 192, 32 * 32), (3, 384, 1536, 16 * 
                (3, 1536, 384, 64), (2, 24, 12, 36), (1, 8, 32, 20), (2, 96, 48, 336 * 496 // 16)]
 
 
+@pytest.mark.timeout(120, method="thread")
+@pytest.mark.parametrize("pipeline", [0, 1], ids=["in_place_stages", "landing_ring"])
 @pytest.mark.parametrize("shape", PROJ_SHAPES)
-def test_projection_gemm_3xtf32(shape):
+def test_projection_gemm_3xtf32(shape, pipeline):
     """glrgtv_proj_gemm / glrgtv_proj_wgrad (tcgen05 kind::tf32, three-pass split, csrc/proj_tc.cu) against fp64 GEMMs:
     fp32-level accuracy for the forward, the input gradient and the weight gradient; ragged tiles (pixels not a multiple of
     128, channels not a multiple of 16 / 32) are zero-padded by the TMA unit"""
-    from imagerestoration_development_unrolling_b200 import ops
+    from imagerestoration_development_unrolling_b200 import ops, _lib as L
+    assert L.load().glrgtv_set_proj_pipeline(pipeline) == 0       # both pipelines of csrc/proj_tc.cu (0 is the default)
+    try:
+        _check_projection(ops, shape)
+    finally:
+        L.load().glrgtv_set_proj_pipeline(0)
+
+
+def _check_projection(ops, shape):
     B, M, K, N = shape
     gen = torch.Generator().manual_seed(M + K)
     w = torch.randn(M, K, generator=gen).cuda().requires_grad_(True)

@@ -1,0 +1,13 @@
+#!/bin/bash
+# landing-ring pipeline of the projection GEMM: accuracy (each shape in its own process, bounded), the GPU tests, timings of both
+# pipelines, a bench line; the four-stream training-step experiment
+set -x
+mkdir -p gpurun_out
+PROJ_PIPELINE=0 timeout 600 python tools/proj_times.py check > gpurun_out/proj_check_ring.log 2>&1; echo "check rc=$?"
+timeout 600 python -m pytest tests/test_gpu_ops.py -x -q -k projection > gpurun_out/gputests_proj.log 2>&1; echo "pytest rc=$?"
+PROJ_PIPELINE=0 timeout 300 python tools/proj_times.py > gpurun_out/proj_times_ring.jsonl 2> gpurun_out/proj_times.err; echo rc=$?
+PROJ_PIPELINE=1 timeout 300 python tools/proj_times.py > gpurun_out/proj_times_inplace.jsonl 2>> gpurun_out/proj_times.err; echo rc=$?
+timeout 300 python bench.py --steps 10 --warmup 3 --no-gpu-baseline --no-cpu-baseline --no-infer4k > gpurun_out/bench_c9.log 2>&1; echo "bench rc=$?"
+timeout 300 python bench.py --steps 10 --warmup 3 --no-gpu-baseline --no-cpu-baseline --no-infer4k --streams > gpurun_out/bench_c9_streams.log 2>&1; echo "bench streams rc=$?"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/gputests_c9.log 2>&1; echo "pytest all rc=$?"
+cat gpurun_out/proj_check_ring.log | cut -c1-200; tail -3 gpurun_out/gputests_proj.log gpurun_out/gputests_c9.log

@@ -19,7 +19,8 @@ BENCH = [(32, 96, 48, 65536), (32, 48, 192, 16384), (32, 96, 48, 16384), (32, 19
 
 def one(shape):
     import torch
-    from imagerestoration_development_unrolling_b200 import ops
+    from imagerestoration_development_unrolling_b200 import ops, _lib as L
+    L.load().glrgtv_set_proj_pipeline(int(os.environ.get("PROJ_PIPELINE", "0")))
     B, M, K, N = shape
     gen = torch.Generator().manual_seed(M + K)
     w = torch.randn(M, K, generator=gen).cuda()
@@ -37,8 +38,10 @@ def one(shape):
 
 def bench():
     import torch
-    from imagerestoration_development_unrolling_b200 import ops
+    from imagerestoration_development_unrolling_b200 import ops, _lib as L
     torch.backends.cuda.matmul.allow_tf32 = False
+    pipe = int(os.environ.get("PROJ_PIPELINE", "0"))        # 0 = in-place stages (default), 1 = landing ring
+    L.load().glrgtv_set_proj_pipeline(pipe)
 
     def t(f, n=10):
         for _ in range(3):
@@ -57,7 +60,7 @@ def bench():
         x = torch.randn(B, K, N, device="cuda")
         gy = torch.randn(B, M, N, device="cuda")
         we = w.unsqueeze(0).expand(B, -1, -1)
-        r = {"shape": (B, M, K, N), "GFLOP": round(2 * B * M * K * N / 1e9, 1)}
+        r = {"pipeline": pipe, "shape": (B, M, K, N), "GFLOP": round(2 * B * M * K * N / 1e9, 1)}
         r["fwd_tc"] = t(lambda: ops.proj_gemm(w, x, False))
         r["fwd_GBs"] = round(4 * B * N * (M + K) / r["fwd_tc"] / 1e6, 0)
         r["fwd_bmm"] = t(lambda: torch.bmm(we, x))
