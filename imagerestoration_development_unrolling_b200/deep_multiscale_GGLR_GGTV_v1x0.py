@@ -225,13 +225,15 @@ class LocalGatedLinearBlock(nn.Module):
         return self.project_out(torch.sigmoid(gate) * gate * val)
 
 
-HOST_CNN_KERNELS = False
+HOST_CNN_KERNELS = True
 
 
 def set_host_cnn_kernels(on: bool) -> bool:
-    """Opt-in: run every LocalNonLinearBlock of the host CNN on libglrgtv's kernels (host_cnn.py: forward under no_grad, forward +
-    backward under autograd) instead of the PyTorch op sequence.  Same results (tests/test_gpu_host_cnn*.py); off by default until
-    the training path has been timed.  Returns the previous setting.  Not used while torch.compile is tracing."""
+    """Every LocalNonLinearBlock of the host CNN on libglrgtv's kernels (host_cnn.py: forward under no_grad, forward + backward
+    under autograd; the 1x1 convolutions on the tcgen05 GEMM) instead of the PyTorch op sequence, for CUDA fp32 inputs whose width
+    is a multiple of 4.  Same results (tests/test_gpu_host_cnn*.py, tests/test_gpu_zz_model_switch.py).  ON by default since it was
+    timed (profiles/r02_configs.md: the whole v13 network's training step at 4 x 256^2 424 -> 109 ms, peak memory 61 -> 21 GB);
+    False restores the module's own PyTorch layers.  Returns the previous setting.  Not used while torch.compile is tracing."""
     global HOST_CNN_KERNELS
     prev, HOST_CNN_KERNELS = HOST_CNN_KERNELS, bool(on)
     return prev

@@ -48,6 +48,24 @@ class CudaCnnKernels:
         return ops.pixel_norm_bwd(x, rs, gx1, gout, s0, nsub)
 
 
+def _mm_t(w: torch.Tensor, g4: torch.Tensor) -> torch.Tensor:
+    """w [nsub, M, K], g4 [B, nsub, M, N] -> [B, nsub, K, N] = w^T g (input gradient of _mm)"""
+    if GEMM != "cublas" and g4.is_cuda and w.shape[0] == 1:
+        from . import ops
+        if ops.proj_supported(w.shape[1], w.shape[2], g4.shape[-1]):
+            return ops.proj_gemm(w[0].contiguous(), g4[:, 0], True).unsqueeze(1)
+    return torch.matmul(w.transpose(-1, -2), g4)
+
+
+def _wgrad(g4: torch.Tensor, x4: torch.Tensor) -> torch.Tensor:
+    """g4 [B, nsub, M, N], x4 [B, nsub, K, N] -> [nsub, M, K] = sum_b g x^T (weight gradient of _mm)"""
+    if GEMM != "cublas" and g4.is_cuda and g4.shape[1] == 1:
+        from . import ops
+        if ops.proj_supported(g4.shape[2], x4.shape[2], g4.shape[-1]):
+            return ops.proj_wgrad(g4[:, 0], x4[:, 0]).unsqueeze(0)
+    return torch.matmul(g4, x4.transpose(-1, -2)).sum(0)
+
+
 def folded_weights(blk) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """(W1' [nsub, 2Hd/nsub, C/nsub], w_dw [2Hd, 9], s1 W2 [nsub, C/nsub, Hd/nsub], s0 [1]) of a LocalNonLinearBlock"""
     nsub = blk.norm.nsubnets
@@ -97,9 +115,9 @@ class _NonLinearBlockFn(torch.autograd.Function):
         w2 = w_out.reshape(nsub, w_out.shape[0] // nsub, w_out.shape[1])
         w9 = w_dw.reshape(-1, 9).contiguous()
         rs = kernels.pixel_rstd(x, nsub, NORM_EPS)
-        h = torch.matmul(w1, x.view(B, nsub, C // nsub, H * W)).view(B, -1, H, W)
+        h = _mm(w1, x.view(B, nsub, C // nsub, H * W)).view(B, -1, H, W)
         u = kernels.dwconv_gate(h, rs, w9, None, None)
-        y = torch.matmul(w2 * skip[1], u.view(B, nsub, -1, H * W)).view(B, C, H, W)
+        y = _mm((w2 * skip[1]).contiguous(), u.view(B, nsub, -1, H * W)).view(B, C, H, W)
         ctx.save_for_backward(x, rs, h, u, w_norm, w_lin, w_dw, w_out, skip)
         ctx.nsub, ctx.kernels = nsub, kernels
         return torch.addcmul(y, x, skip[0:1])
@@ -117,13 +135,13 @@ class _NonLinearBlockFn(torch.autograd.Function):
         w2 = w_out.reshape(nsub, w_out.shape[0] // nsub, w_out.shape[1])
         g4, u4, x4 = gout.view(B, nsub, C // nsub, N), u.view(B, nsub, -1, N), x.view(B, nsub, C // nsub, N)
         # out = s0 x + s1 W2 u
-        gw2_raw = torch.matmul(g4, u4.transpose(-1, -2)).sum(0)                              # [nsub, C/nsub, Hd/nsub] = sum gout u^T
+        gw2_raw = _wgrad(g4, u4)                                                             # [nsub, C/nsub, Hd/nsub] = sum gout u^T
         g_skip = torch.stack([torch.dot(gout.reshape(-1), x.reshape(-1)), (gw2_raw * w2).sum()])
-        gu = torch.matmul((w2 * skip[1]).transpose(-1, -2), g4).view(B, -1, H, W)            # [B, Hd, H, W]
+        gu = _mm_t((w2 * skip[1]).contiguous(), g4).view(B, -1, H, W)                        # [B, Hd, H, W]
         gh, gw9 = kernels.dwconv_gate_bwd(h, rs, w_dw.reshape(-1, 9).contiguous(), gu)
         gh4 = gh.view(B, nsub, -1, N)
-        gw1f = torch.matmul(gh4, x4.transpose(-1, -2)).sum(0)                                # [nsub, 2Hd/nsub, C/nsub]
-        gx1 = torch.matmul(w1f.transpose(-1, -2), gh4).view(B, C, H, W)
+        gw1f = _wgrad(gh4, x4)                                                               # [nsub, 2Hd/nsub, C/nsub]
+        gx1 = _mm_t(w1f, gh4).view(B, C, H, W)
         gx = kernels.pixel_norm_bwd(x, rs, gx1, gout, skip[0:1], nsub)
         return (gx, (gw1f * w1).sum(1).reshape(w_norm.shape), (gw1f * wn).reshape(w_lin.shape), gw9.reshape(w_dw.shape),
                 (gw2_raw * skip[1]).reshape(w_out.shape), g_skip, None, None)

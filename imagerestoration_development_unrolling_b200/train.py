@@ -200,11 +200,11 @@ def train(conf: dict, device: Optional[torch.device] = None, on_step: Optional[C
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     tc = dict(total_iters=1000, checkpoint_every=5000, log_every=100, verbose_rate=1000, num_workers=0, optimizer=None,
-              w_mse=0.1, w_stab=0.5, latent_sigma=0.05, host_cnn_kernels=False, validate_every=0)
+              w_mse=0.1, w_stab=0.5, latent_sigma=0.05, host_cnn_kernels=True, validate_every=0)
     tc.update(conf.get("train") or {})
-    if tc["host_cnn_kernels"]:        # opt-in: the host CNN's LocalNonLinearBlocks on libglrgtv as well (host_cnn.py)
-        from . import deep_multiscale_GGLR_GGTV_v1x0 as v13
-        v13.set_host_cnn_kernels(True)
+    # the host CNN's LocalNonLinearBlocks on libglrgtv as well (host_cnn.py; the default) or on the module's own PyTorch layers
+    from . import deep_multiscale_GGLR_GGTV_v1x0 as v13
+    v13.set_host_cnn_kernels(bool(tc["host_cnn_kernels"]))
     seed = int(conf.get("manual_seed", 2204))
     torch.manual_seed(seed)                                          # same initial weights on every rank
     device = device or (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))

@@ -153,15 +153,16 @@ def test_nonlinear_block_gradients_match_autograd(dim, hidden, nsub, B, H, W):
 
 
 def test_switch_is_a_noop_for_cpu_tensors():
-    """the opt-in switch only reroutes CUDA float32 inputs; CPU tensors keep the PyTorch op sequence (the host CNN is not the
-    library's hot path, so it may run anywhere the reference's does)"""
+    """the switch (on by default) only reroutes CUDA float32 inputs; CPU tensors keep the PyTorch op sequence whatever it says (the
+    host CNN is not the library's hot path, so it may run anywhere the reference's does)"""
     blk = _block(8, 8, 1, seed=2)
     x = torch.randn(1, 8, 6, 8)
     with torch.no_grad():
-        ref = blk(x)
-        prev = M.set_host_cnn_kernels(True)
+        prev = M.set_host_cnn_kernels(False)
         try:
+            ref = blk(x)
+            M.set_host_cnn_kernels(True)
             got = blk(x)
         finally:
             M.set_host_cnn_kernels(prev)
-    assert prev is False and torch.equal(got, ref)
+    assert prev is True and torch.equal(got, ref)
