@@ -119,6 +119,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+// fp32 -> TF32 hi part (round to nearest) + fp32 remainder
+__device__ __forceinline__ void pt_split1(const float4 v, float4& h, float4& l) {
+    uint32_t hx, hy, hz, hw;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hz) : "f"(v.z));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hw) : "f"(v.w));
+    h.x = __uint_as_float(hx); h.y = __uint_as_float(hy); h.z = __uint_as_float(hz); h.w = __uint_as_float(hw);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+}
+// raw -> hi | lo for the 16-byte pieces t, t + 128, ... < n4 of a tile (128 splitter threads; `raw` may be `hi`: in place), position
+// for position so that the TMA swizzle is preserved.  Four loads in flight per thread: the first version's one-at-a-time loop left
+// the splitter warps ~3/4 busy and close to being the weight-gradient kernel's limiter (profiles/r02_proj_stalls.md).
+__device__ __forceinline__ void pt_split(const float4* raw, float4* hi, float4* lo, int t, int n4) {
+    int i = t;
+    for (; i + 384 < n4; i += 512) {
+        const float4 v0 = raw[i], v1 = raw[i + 128], v2 = raw[i + 256], v3 = raw[i + 384];
+        float4 h, l;
+        pt_split1(v0, h, l); hi[i] = h; lo[i] = l;
+        pt_split1(v1, h, l); hi[i + 128] = h; lo[i + 128] = l;
+        pt_split1(v2, h, l); hi[i + 256] = h; lo[i + 256] = l;
+        pt_split1(v3, h, l); hi[i + 384] = h; lo[i + 384] = l;
+    }
+    for (; i < n4; i += 128) {
+        float4 h, l;
+        pt_split1(raw[i], h, l); hi[i] = h; lo[i] = l;
+    }
+}
+// the activation tile of a K-tail stage: four boxes of [32 k rows][32 pixels] of which only the first `krows` rows are read by
+// the MMAs (a multiple of 8: whole k-steps) - the valid pieces are a prefix of EACH 4 KB box
+__device__ __forceinline__ void pt_split_ktail(const float4* raw, float4* hi, float4* lo, int t, int krows) {
+    const int per = krows * 8;
+    for (int i = t; i < 4 * per; i += 128) {
+        const int box = i / per, idx = box * 256 + (i - box * per);
+        float4 h, l;
+        pt_split1(raw[idx], h, l); hi[idx] = h; lo[idx] = l;
+    }
+}
+
 struct PtSmem {
     int NC, stages;
     __host__ __device__ size_t a_bytes() const { return 128 * PT_STAGE_K * 4; }                 // 16 KB
@@ -316,7 +355,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_proj_tc(const __grid_constant
         // ------------------------------------------------------------------ splitter (128 threads)
         const int t = (int)threadIdx.x - 256;
         long it = 0;
-        const int nb4 = MODE == 0 ? 0 : (int)(lay.b_bytes() / 16);
         for (long u = blockIdx.x; u < a.units; u += gridDim.x) {
             const PtUnit un = pt_unit(a, u);
             for (long q = un.q0; q < un.q1; ++q, ++it) {
@@ -324,23 +362,19 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_proj_tc(const __grid_constant
                 const uint32_t ph = (uint32_t)((it / S) & 1);
                 bar_wait(FULL(s), ph);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
-                auto split4 = [&](float4* hi, float4* lo, int n4) {
-                    for (int i = t; i < n4; i += 128) {
-                        const float4 v = hi[i];
-                        float4 h, l;
-                        uint32_t hx, hy, hz, hw;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hz) : "f"(v.z));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hw) : "f"(v.w));
-                        h.x = __uint_as_float(hx); h.y = __uint_as_float(hy); h.z = __uint_as_float(hz); h.w = __uint_as_float(hw);
-                        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                        hi[i] = h;
-                        lo[i] = l;
-                    }
-                };
-                split4((float4*)st, (float4*)(st + lay.a_bytes()), (int)(lay.a_bytes() / 16));
-                if (MODE == 1) split4((float4*)(st + lay.b_off()), (float4*)(st + lay.blo_off()), nb4);
+                float4* const ahi = (float4*)st;
+                float4* const alo = (float4*)(st + lay.a_bytes());
+                if (MODE == 0) {
+                    const int left = a.Kred - (int)q * PT_STAGE_K;                    // valid k rows of this stage (whole k-steps)
+                    if (left >= PT_STAGE_K) pt_split(ahi, ahi, alo, t, (int)(lay.a_bytes() / 16));
+                    else pt_split_ktail(ahi, ahi, alo, t, (left + 7) & ~7);
+                } else {
+                    // rows of gY / channels of X beyond the matrix only feed accumulator rows / columns that are never stored
+                    const int rows = a.M - un.tile * 128 < 128 ? a.M - un.tile * 128 : 128;
+                    const int n0 = un.chunk * a.NC, cols = a.Nout - n0 < a.NC ? a.Nout - n0 : a.NC;
+                    pt_split(ahi, ahi, alo, t, rows * 8);
+                    pt_split((float4*)(st + lay.b_off()), (float4*)(st + lay.b_off()), (float4*)(st + lay.blo_off()), t, cols * 8);
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 bar_arrive(SPLIT(s));
             }
@@ -508,7 +542,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_proj_tc2(const __grid_constan
         // ------------------------------------------------------------------ splitter (128 threads): LAND[l] -> OPER[o] hi | lo
         const int t = (int)threadIdx.x - 256;
         long it = 0;
-        const int na4 = (int)(a_bytes / 16), nb4 = MODE == 0 ? 0 : (int)(b_bytes / 16);
+        const int na4 = (int)(a_bytes / 16);
         for (long u = blockIdx.x; u < a.units; u += gridDim.x) {
             const PtUnit un = pt_unit(a, u);
             for (long q = un.q0; q < un.q1; ++q, ++it) {
@@ -517,23 +551,16 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_proj_tc2(const __grid_constan
                 bar_wait(OEMPTY(o), (uint32_t)((it / SO) & 1) ^ 1u);
                 const uint8_t* src = smem + lay.land_off() + (size_t)l * land_bytes;
                 uint8_t* dst = smem + (size_t)o * oper_bytes;
-                auto split4 = [&](const float4* raw, float4* hi, float4* lo, int n4) {
-                    for (int i = t; i < n4; i += 128) {
-                        const float4 v = raw[i];
-                        float4 h, lw;
-                        uint32_t hx, hy, hz, hw;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hz) : "f"(v.z));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hw) : "f"(v.w));
-                        h.x = __uint_as_float(hx); h.y = __uint_as_float(hy); h.z = __uint_as_float(hz); h.w = __uint_as_float(hw);
-                        lw.x = v.x - h.x; lw.y = v.y - h.y; lw.z = v.z - h.z; lw.w = v.w - h.w;
-                        hi[i] = h;
-                        lo[i] = lw;
-                    }
-                };
-                split4((const float4*)src, (float4*)dst, (float4*)(dst + a_bytes), na4);
-                if (MODE == 1) split4((const float4*)(src + a_bytes), (float4*)(dst + 2 * a_bytes), (float4*)(dst + 2 * a_bytes + b_pad), nb4);
+                if (MODE == 0) {
+                    const int left = a.Kred - (int)q * PT_STAGE_K;
+                    if (left >= PT_STAGE_K) pt_split((const float4*)src, (float4*)dst, (float4*)(dst + a_bytes), t, na4);
+                    else pt_split_ktail((const float4*)src, (float4*)dst, (float4*)(dst + a_bytes), t, (left + 7) & ~7);
+                } else {
+                    const int rows = a.M - un.tile * 128 < 128 ? a.M - un.tile * 128 : 128;
+                    const int n0 = un.chunk * a.NC, cols = a.Nout - n0 < a.NC ? a.Nout - n0 : a.NC;
+                    pt_split((const float4*)src, (float4*)dst, (float4*)(dst + a_bytes), t, rows * 8);
+                    pt_split((const float4*)(src + a_bytes), (float4*)(dst + 2 * a_bytes), (float4*)(dst + 2 * a_bytes + b_pad), t, cols * 8);
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 bar_arrive(OSPLIT(o));
                 bar_arrive(LEMPTY(l));
