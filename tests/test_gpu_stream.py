@@ -299,3 +299,25 @@ def test_automatic_forward_choice(M, lib, scale):
         out0 = blk(x)
         assert lib.glrgtv_stream_launch_count() - n0 == [4, 6, 8, 8][scale]
     assert rel(out0, out1) < 2e-6, rel(out0, out1)
+
+
+@pytest.mark.parametrize("streams", [False, True])
+def test_lockstep_filtering_single_rank(M, lib, streams):
+    """shard.sharded_filtering_staged with world = 1 through the CUDA stage runners (prepared calls, one CUDA stream per scale,
+    strips used in place inside their halo-room buffers, row-view outputs) equals the blocks called directly"""
+    from imagerestoration_development_unrolling_b200 import shard
+    dims, Gs = [12, 24], [2, 2]
+    blks = [make_block(M, d, g, random_block_state(d, g, seed=90 + i)) for i, (d, g) in enumerate(zip(dims, Gs))]
+    xs = []
+    for i, d in enumerate(dims):
+        x = shard.strip_with_halo_room((1, d, 64 >> i, 80 >> i), 0, 1, device="cuda")
+        x.copy_(torch.randn(1, d, 64 >> i, 80 >> i, generator=torch.Generator().manual_seed(i)).cuda())
+        xs.append(x)
+    lib.glrgtv_set_fwd_kernels(0)
+    with torch.no_grad():
+        ref = [blk(x) for blk, x in zip(blks, xs)]
+        got = shard.sharded_filtering_staged(blks, xs, 0, 1, runners=[shard.CudaStageRunner(b) for b in blks], streams=streams)
+        also = shard.sharded_filtering_staged(blks, xs, 0, 1, streams=streams)          # one rank without runners: the blocks as they are
+    torch.cuda.synchronize()
+    for r, g, a in zip(ref, got, also):
+        assert rel(g, r) < 1e-6 and torch.equal(a, r)
