@@ -239,16 +239,17 @@ def set_host_cnn_kernels(on: bool) -> bool:
     return prev
 
 
-FILTER_STREAMS = False
+FILTER_STREAMS = True
 _side_streams = {}
 
 
 def set_filter_streams(on: bool) -> bool:
-    """Opt-in: `AbtractMultiScaleGraphFilter.filtering` runs its four LocalLowpassFilteringBlocks on four CUDA streams (the
-    caller's stream + three side streams, fork / join by events) - the blocks are independent (V1X0:1117-1131).  The same
-    kernels and results; it shortens the latency of small batches, where one block cannot fill 148 SMs (tools/bench_config1.py),
-    and it is capturable in a CUDA graph.  Autograd runs each block's backward on the stream its forward ran on.  Returns the
-    previous setting."""
+    """`AbtractMultiScaleGraphFilter.filtering` runs its four LocalLowpassFilteringBlocks on four CUDA streams (the caller's
+    stream + three side streams, fork / join by events) - the blocks are independent (V1X0:1117-1131).  The same kernels and
+    results; it shortens the latency of small batches, where one block cannot fill 148 SMs (config 1: 1.19 -> 0.61 ms inside a
+    CUDA graph), overlaps the tails of large ones (the bench's training step: 31.3 -> 28.5 ms) and is capturable in a CUDA graph.
+    Autograd runs each block's backward on the stream its forward ran on.  ON by default for CUDA inputs (not while
+    torch.compile is tracing); False runs the blocks one after the other.  Returns the previous setting."""
     global FILTER_STREAMS
     prev, FILTER_STREAMS = FILTER_STREAMS, bool(on)
     return prev

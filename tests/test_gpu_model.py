@@ -111,7 +111,7 @@ def test_executor_on_a_cbsd68_sized_image(golden_dir):
 
 @pytest.mark.gpu
 def test_four_stream_filtering_equals_the_sequential_blocks(golden_dir):
-    """set_filter_streams(True): the four filter blocks on four streams (V1X0:1117-1131: independent) - the same outputs bit for
+    """set_filter_streams(True), the default: the four filter blocks on four streams (V1X0:1117-1131: independent) - the same outputs bit for
     bit, the same gradients up to the order of the floating-point atomics, also when captured into a CUDA graph"""
     from imagerestoration_development_unrolling_b200 import deep_multiscale_GGLR_GGTV_v1x0 as M
     z = _load(golden_dir)
@@ -126,9 +126,10 @@ def test_four_stream_filtering_equals_the_sequential_blocks(golden_dir):
         grads = torch.autograd.grad(out.square().mean(), params)
         return out.detach(), grads
 
-    out1, g1 = run()
-    prev = M.set_filter_streams(True)
+    prev = M.set_filter_streams(False)
     try:
+        out1, g1 = run()
+        M.set_filter_streams(True)
         out2, g2 = run()
         with torch.no_grad():
             m(noisy)
