@@ -98,8 +98,11 @@ __device__ __forceinline__ WWGeom ww_geom(const WWArgs& a) {
 // ---------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------
+#ifndef WW_FWD_MINB
+#define WW_FWD_MINB 4
+#endif
 template <int FT, int PX>
-__global__ void __launch_bounds__(WW_NT, 4) k_weights_walk(WWArgs a) {
+__global__ void __launch_bounds__(WW_NT, WW_FWD_MINB) k_weights_walk(WWArgs a) {
     const int H = a.s.H, W = a.s.W, G = a.s.G, C = G * FT;
     const size_t HW = (size_t)H * W;
     const WWGeom q = ww_geom<PX>(a);
