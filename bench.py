@@ -437,6 +437,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
 
+    # what the host -> device link delivers for these inputs on their own (explains e2e when the step is shorter than the copy)
+    torch.cuda.synchronize()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        h0.record(copy_stream)
+        for _ in range(3):
+            for h, d in zip(hx[0], dbuf[0]):
+                d.copy_(h, non_blocking=True)
+        h1.record(copy_stream)
+    torch.cuda.synchronize()
+    h2d_ms = h0.elapsed_time(h1) / 3
+
     i4k = None if a.no_infer4k else infer4k(blocks, dev, rank, world)
 
     if rank == 0:
@@ -482,6 +494,7 @@ def main():
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": int(sum(h.numel() for h in hx[0]) * 4), "d2h_bytes_per_step": 4,
+                    "h2d_copy_alone_ms": round(h2d_ms, 3), "h2d_copy_alone_GBs": round(sum(h.numel() for h in hx[0]) * 4 / h2d_ms / 1e6, 1),
                     "note": "pinned-host inputs of step i+1 are copied on a side stream while step i computes; the loss of step i is copied "
                             "to pinned host memory and consumed by the host while step i+1 is enqueued; at N > 1 the ranks' copies "
                             "(755 MB per rank and step: feature maps, not images) share the host's memory channels and PCIe root complexes"},
