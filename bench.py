@@ -309,14 +309,21 @@ def main():
 
     side = None if a.no_streams else [torch.cuda.Stream(device=dev) for _ in blocks]
 
-    def step(inputs, serial=False):
+    def step(inputs, serial=False, ready=None):
+        """ready: one event per input (its host -> device copy); a block waits only for its OWN input"""
         if side is None or serial:
-            outs = [blk(x) for blk, x in zip(blocks, inputs)]
+            outs = []
+            for i, (blk, x) in enumerate(zip(blocks, inputs)):
+                if ready is not None:
+                    torch.cuda.current_stream().wait_event(ready[i])
+                outs.append(blk(x))
         else:                                           # V1X0:1117-1131: the four blocks are independent (autograd runs each block's
             cur = torch.cuda.current_stream()           # backward on the stream its forward ran on and joins them at the end)
             outs = []
-            for st, blk, x in zip(side, blocks, inputs):
+            for i, (st, blk, x) in enumerate(zip(side, blocks, inputs)):
                 st.wait_stream(cur)
+                if ready is not None:
+                    st.wait_event(ready[i])
                 with torch.cuda.stream(st):
                     outs.append(blk(x))
             for st in side:
@@ -382,16 +389,16 @@ def main():
     hx = [[torch.randn(sh).pin_memory() for sh in shapes] for _ in range(2)]
     dbuf = [[torch.empty(sh, device=dev) for sh in shapes] for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    copied = [[torch.cuda.Event() for _ in shapes] for _ in range(2)]     # one event per input tensor: a block starts when ITS map is in
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
     def start_copy(i):
         k = i & 1
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[k])          # the step that last read this buffer has finished
-            for h, d in zip(hx[k], dbuf[k]):
+            for h, d, ev in zip(hx[k], dbuf[k], copied[k]):      # largest map first: its block is more than half of the step
                 d.copy_(h, non_blocking=True)
-            copied[k].record(copy_stream)
+                ev.record(copy_stream)
 
     # the step's result (its loss) goes to pinned host memory every step; the host consumes the value of step i while step i+1 is
     # already enqueued (one event per buffer), so the read-back does not drain the GPU between steps - what an asynchronous training
@@ -402,11 +409,10 @@ def main():
 
     def e2e_step(i, n):
         k = i & 1
-        torch.cuda.current_stream().wait_event(copied[k])
         if i + 1 < n:
             start_copy(i + 1)
         ins = [d.detach().requires_grad_(True) for d in dbuf[k]]
-        outs = step(ins)
+        outs = step(ins, ready=copied[k])
         loss = sum(o.mean() for o in outs)
         consumed[k].record(torch.cuda.current_stream())
         loss_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)       # D2H read of the step's result
