@@ -351,8 +351,11 @@ __device__ __forceinline__ void bw_walk(const StreamBwdArgs& a, float* smem, con
             auto z_lr = [&](const Row& zc, int back, float& l, float& r) {
                 if (FINE) {
                     const float* p = zring + zslot(back) * Wp + lcol;
-                    l = lc.first ? zc.v[0] : p[-1];
-                    r = lc.last ? zc.v[3] : p[4];
+                    // (the first / last lane of a column strip inside the image owns halo columns whose results are thrown away: it
+                    // takes its own value instead of reading the ring element next door - for row slot 0 of channel 0 that would be
+                    // the word BEFORE the shared-memory block, tools/emu_asan.sh)
+                    l = (lc.first || lcol == 0) ? zc.v[0] : p[-1];
+                    r = (lc.last || lcol + 4 >= Wp) ? zc.v[3] : p[4];
                 } else {
                     nb_lr<false, false>(zc, l, r, lc, 0);
                 }
