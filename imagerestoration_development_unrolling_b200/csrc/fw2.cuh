@@ -247,7 +247,9 @@ __global__ void __launch_bounds__(B2_MAXT, MODE == FW_X2 ? 1 : 2) k_fw2(F2Args a
         // ---- first-level stencils at row t-1 (s clamp-extended)
         {
             const float2 z0 = pld(zsig + zt), z1 = pld(zsig + o1), z2 = pld(zsig + o2);
-            const float2 z1l = pshl(z1, lc.first ? z1.x : zsig[o1 - 1]), z1r = pshr(z1, lc.last ? z1.y : zsig[o1 + 2]);
+            // (the first / last lane of a column strip's window owns halo columns: it takes its own value instead of the ring word
+            // next door, which for channel 0 / slot 0 would be the word before the shared-memory block - tools/emu_asan.sh)
+            const float2 z1l = pshl(z1, (lc.first || col0 == 0) ? z1.x : zsig[o1 - 1]), z1r = pshr(z1, (lc.last || col0 + 2 >= RW) ? z1.y : zsig[o1 + 2]);
             sT[N] = b2_S(kT, z1, z2, z0, z1l, z1r);
             if (HAS_L) sL[N] = b2_S(kL, z1, z2, z0, z1l, z1r);
             const int r = t - 1;
